@@ -1,0 +1,101 @@
+/*
+ * msda_b200.h -- C ABI of the B200 (sm_100a) multi-scale deformable attention library
+ * (libmsda_b200.so).  Plain pointers and sizes only; no torch types.
+ *
+ * Every entry point replaces a piece of the reference's compiled extension
+ * `MultiScaleDeformableAttention` (timmeinhardt/trackformer @ e468bf1,
+ * paths relative to src/trackformer/models/ops/):
+ *
+ *   msda_b200_forward_{f32,f64}   <- ms_deform_attn_cuda_forward          src/cuda/ms_deform_attn_cuda.cu:19-86
+ *                                    (= ms_deformable_im2col_cuda         src/cuda/ms_deform_im2col_cuda.cuh:380-410
+ *                                       + at::sum over the L*P columns    src/cuda/ms_deform_attn_cuda.cu:80)
+ *   msda_b200_backward_{f32,f64}  <- ms_deform_attn_cuda_backward         src/cuda/ms_deform_attn_cuda.cu:89-168
+ *                                    (= ms_deformable_col2im_coord_cuda   src/cuda/ms_deform_im2col_cuda.cuh:454-496
+ *                                       + ms_deformable_col2im_cuda       src/cuda/ms_deform_im2col_cuda.cuh:412-452)
+ *   msda_b200_*_host_*            <- the same two calls for callers that hold HOST buffers (the
+ *                                    reference has no such path: its CPU entry throws,
+ *                                    src/cpu/ms_deform_attn_cpu.cpp:15,27); used for end-to-end timing.
+ *
+ * The Python-visible module built on top of this ABI keeps the reference's pybind surface
+ * (src/vision.cpp:4-7, src/ms_deform_attn.h:10-50): see trackformer_b200/csrc/msda_torch.cpp.
+ *
+ * Tensor layouts (contiguous, last index fastest) -- identical to the reference:
+ *   value           [N][S][M][D]      s = level_start[l] + y*W_l + x,  S = sum_l H_l*W_l
+ *   spatial_shapes  [L][2] int64      (H_l, W_l), DEVICE memory (the reference keeps it on the GPU,
+ *                                     models/deformable_transformer.py:156); level starts are derived
+ *                                     in-kernel, the old 5-argument API has no level_start_index
+ *   sampling_loc    [N][Lq][M][L][P][2]   (x, y) normalised to [0,1] over the padded level
+ *   attn_weight     [N][Lq][M][L][P]
+ *   output / grad_output                  [N][Lq][M*D]
+ *   grad_value / grad_sampling_loc / grad_attn_weight : shapes of value / sampling_loc / attn_weight
+ *
+ * Ownership: the caller owns every buffer.  The backward call zero-fills grad_value itself
+ * (the reference does at::zeros_like, ms_deform_attn_cuda.cu:119) and overwrites the other two.
+ * All work is enqueued on `stream` (a cudaStream_t, passed as void*; NULL = legacy default
+ * stream); the device-pointer calls never synchronise.  Re-entrant, no global state.
+ *
+ * Errors: every function returns 0 on success, a negative MSDA_E_* code for argument
+ * errors, or a positive cudaError_t value when a CUDA call / kernel launch failed (the
+ * reference only printf()s launch errors, ms_deform_im2col_cuda.cuh:404-408 -- here they are
+ * returned, and the Python binding raises).  msda_b200_error_string() renders either kind.
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_B200_ABI_VERSION 1
+
+#define MSDA_E_NULLPTR   (-1)  /* a required pointer is NULL                       */
+#define MSDA_E_DIMS      (-2)  /* a dimension is <= 0 (N, Lq may be 0: no-op)      */
+#define MSDA_E_TOO_LARGE (-3)  /* a per-sample slab exceeds 2^31-1 elements        */
+#define MSDA_E_LEVELS    (-4)  /* L > MSDA_B200_MAX_LEVELS                         */
+
+#define MSDA_B200_MAX_LEVELS 32
+
+int msda_b200_abi_version(void);
+const char* msda_b200_error_string(int code);
+
+/* ---- device-pointer entry points (the hot path) -------------------------------------- */
+int msda_b200_forward_f32(const float* value, const int64_t* spatial_shapes,
+                          const float* sampling_loc, const float* attn_weight, float* output,
+                          int N, int S, int M, int D, int L, int Lq, int P, void* stream);
+int msda_b200_forward_f64(const double* value, const int64_t* spatial_shapes,
+                          const double* sampling_loc, const double* attn_weight, double* output,
+                          int N, int S, int M, int D, int L, int Lq, int P, void* stream);
+
+int msda_b200_backward_f32(const float* value, const int64_t* spatial_shapes,
+                           const float* sampling_loc, const float* attn_weight,
+                           const float* grad_output, float* grad_value, float* grad_sampling_loc,
+                           float* grad_attn_weight,
+                           int N, int S, int M, int D, int L, int Lq, int P, void* stream);
+int msda_b200_backward_f64(const double* value, const int64_t* spatial_shapes,
+                           const double* sampling_loc, const double* attn_weight,
+                           const double* grad_output, double* grad_value, double* grad_sampling_loc,
+                           double* grad_attn_weight,
+                           int N, int S, int M, int D, int L, int Lq, int P, void* stream);
+
+/* ---- host-buffer entry points (H2D + kernel + D2H inside the call; synchronous) -------- */
+int msda_b200_forward_host_f32(const float* value, const int64_t* spatial_shapes,
+                               const float* sampling_loc, const float* attn_weight, float* output,
+                               int N, int S, int M, int D, int L, int Lq, int P, int device);
+int msda_b200_backward_host_f32(const float* value, const int64_t* spatial_shapes,
+                                const float* sampling_loc, const float* attn_weight,
+                                const float* grad_output, float* grad_value,
+                                float* grad_sampling_loc, float* grad_attn_weight,
+                                int N, int S, int M, int D, int L, int Lq, int P, int device);
+
+/* ---- introspection / tuning (not part of the reference surface) ------------------------ */
+/* Selects a kernel variant for experiments (0 = library default). Process-wide.            */
+void msda_b200_set_variant(int fwd_variant, int bwd_variant);
+/* Number of kernel launches this library has enqueued since load (bench.py's gpu_launches). */
+uint64_t msda_b200_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

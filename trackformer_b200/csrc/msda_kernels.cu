@@ -1,0 +1,466 @@
+// libmsda_b200: hand-written sm_100a kernels for multi-scale deformable attention
+// (forward + fused backward) behind the C ABI declared in include/msda_b200.h.
+//
+// Replaces the reference's three kernels + host wrappers
+//   ms_deformable_im2col_gpu_kernel        ms_deform_im2col_cuda.cuh:165-237  (+ at::sum, ms_deform_attn_cuda.cu:80)
+//   ms_deformable_col2im_gpu_kernel        ms_deform_im2col_cuda.cuh:239-306
+//   ms_deformable_col2im_coord_gpu_kernel  ms_deform_im2col_cuda.cuh:308-378
+// with ONE forward kernel (no L*P-times inflated `columns` tensor, no separate reduction,
+// level starts derived in-kernel) and ONE backward kernel (corners are read once and feed
+// grad_value, grad_sampling_loc and grad_attn_weight together).
+//
+// Work decomposition ("group" = one (n, q, m) triple = one head of one query):
+//   * G lanes of a warp own a group; lane j owns channel packs j, j+G, ... (ITERS of them),
+//     each pack = VEC contiguous channels = 16 bytes when the layout allows.  For the shipped
+//     geometry (fp32, D=32) G=8, VEC=4: the 8 lanes of a group read one full 128-byte row of
+//     `value` per bilinear corner -> every warp-level load touches exactly 4 full L1 lines.
+//   * groups are numbered n-major, then q, then m, i.e. exactly the memory order of
+//     sampling_loc / attn_weight / output, so those streams are read/written fully coalesced.
+//   * backward: per-sample partial dot products are reduced over the G lanes with
+//     warp shuffles; grad_value uses 128-bit vector reductions (red.global.add.v4.f32).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/msda_b200.h"
+#include "msda_common.cuh"
+#include "msda_fwd_d32.cuh"
+
+namespace msda {
+
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_fwd_variant{0};
+static std::atomic<int> g_bwd_variant{0};
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------
+// Forward: out[n,q,m,:] = sum_{l,p} attn * bilinear(value_l, loc)
+// ------------------------------------------------------------------------------------
+template <typename T, int VEC, int G, int ITERS>
+__global__ void __launch_bounds__(kThreads)
+msda_fwd_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
+                const T* __restrict__ loc, const T* __restrict__ attn, T* __restrict__ out,
+                int S, int M, int D, int L, int Lq, int P, int64_t groups) {
+  const int64_t gid_raw = (int64_t(blockIdx.x) * kThreads + threadIdx.x) / G;
+  const int lane = threadIdx.x % G;
+  const bool active = gid_raw < groups;
+  const int64_t gid = active ? gid_raw : groups - 1;
+
+  const int m = int(gid % M);
+  const int64_t n = gid / (int64_t(M) * Lq);
+  const int stride = M * D;
+  const int npacks = D / VEC;
+
+  const T* vhead = value + n * int64_t(S) * stride + m * D;
+  const T* lp = loc + gid * (int64_t(L) * P * 2);
+  const T* ap = attn + gid * (int64_t(L) * P);
+
+  Pack<T, VEC> acc[ITERS];
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) acc[i] = pack_zero<T, VEC>();
+
+  int64_t start = 0;
+  for (int l = 0; l < L; ++l) {
+    const int H = int(__ldg(shapes + 2 * l));
+    const int W = int(__ldg(shapes + 2 * l + 1));
+    const T* vl = vhead + start * stride;
+    start += int64_t(H) * W;
+    for (int p = 0; p < P; ++p) {
+      const T lx = __ldg(lp), ly = __ldg(lp + 1), a = __ldg(ap);
+      lp += 2;
+      ap += 1;
+      const Tap<T> t = make_tap<T>(lx, ly, H, W, stride);
+      if (!t.live) continue;
+      const T a1 = t.w1 * a, a2 = t.w2 * a, a3 = t.w3 * a, a4 = t.w4 * a;
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) {
+        const int pk = lane + i * G;
+        if (pk >= npacks) break;
+        const int co = pk * VEC;
+        const Pack<T, VEC> v1 = t.k1 ? ldg_pack<T, VEC>(vl + t.o1 + co) : pack_zero<T, VEC>();
+        const Pack<T, VEC> v2 = t.k2 ? ldg_pack<T, VEC>(vl + t.o2 + co) : pack_zero<T, VEC>();
+        const Pack<T, VEC> v3 = t.k3 ? ldg_pack<T, VEC>(vl + t.o3 + co) : pack_zero<T, VEC>();
+        const Pack<T, VEC> v4 = t.k4 ? ldg_pack<T, VEC>(vl + t.o4 + co) : pack_zero<T, VEC>();
+#pragma unroll
+        for (int c = 0; c < VEC; ++c)
+          acc[i].v[c] += a1 * v1.v[c] + a2 * v2.v[c] + a3 * v3.v[c] + a4 * v4.v[c];
+      }
+    }
+  }
+  if (active) {
+    T* o = out + gid * D;
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int pk = lane + i * G;
+      if (pk < npacks) st_pack<T, VEC>(o + pk * VEC, acc[i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Backward (fused): grad_value (vector reductions), grad_sampling_loc, grad_attn_weight
+// ------------------------------------------------------------------------------------
+template <typename T, int G>
+__device__ __forceinline__ T group_sum(T v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T, int VEC, int G, int ITERS>
+__global__ void __launch_bounds__(kThreads)
+msda_bwd_kernel(const T* __restrict__ value, const int64_t* __restrict__ shapes,
+                const T* __restrict__ loc, const T* __restrict__ attn,
+                const T* __restrict__ grad_out, T* __restrict__ grad_value,
+                T* __restrict__ grad_loc, T* __restrict__ grad_attn,
+                int S, int M, int D, int L, int Lq, int P, int64_t groups) {
+  const int64_t gid_raw = (int64_t(blockIdx.x) * kThreads + threadIdx.x) / G;
+  const int lane = threadIdx.x % G;
+  const bool active = gid_raw < groups;
+  const int64_t gid = active ? gid_raw : groups - 1;
+
+  const int m = int(gid % M);
+  const int64_t n = gid / (int64_t(M) * Lq);
+  const int stride = M * D;
+  const int npacks = D / VEC;
+
+  const int64_t head_ofs = n * int64_t(S) * stride + m * D;
+  const T* vhead = value + head_ofs;
+  T* gvhead = grad_value + head_ofs;
+  const int64_t sbase = gid * (int64_t(L) * P);
+  const T* lp = loc + sbase * 2;
+  const T* ap = attn + sbase;
+  T* glp = grad_loc + sbase * 2;
+  T* gap = grad_attn + sbase;
+
+  Pack<T, VEC> g[ITERS];
+#pragma unroll
+  for (int i = 0; i < ITERS; ++i) {
+    const int pk = lane + i * G;
+    g[i] = (active && pk < npacks) ? ldg_pack<T, VEC>(grad_out + gid * D + pk * VEC)
+                                   : pack_zero<T, VEC>();
+  }
+
+  int64_t start = 0;
+  for (int l = 0; l < L; ++l) {
+    const int H = int(__ldg(shapes + 2 * l));
+    const int W = int(__ldg(shapes + 2 * l + 1));
+    const int64_t lofs = start * stride;
+    start += int64_t(H) * W;
+    for (int p = 0; p < P; ++p) {
+      const T lx = __ldg(lp), ly = __ldg(lp + 1), a = __ldg(ap);
+      const Tap<T> t = make_tap<T>(lx, ly, H, W, stride);
+      T s_a = T(0), s_x = T(0), s_y = T(0);
+      if (t.live) {  // uniform across the G lanes of a group
+        const T hx = T(1) - t.lx, hy = T(1) - t.ly;
+        const T a1 = t.w1 * a, a2 = t.w2 * a, a3 = t.w3 * a, a4 = t.w4 * a;
+#pragma unroll
+        for (int i = 0; i < ITERS; ++i) {
+          const int pk = lane + i * G;
+          if (pk >= npacks) break;
+          const int co = pk * VEC;
+          const T* vl = vhead + lofs + co;
+          const Pack<T, VEC> v1 = t.k1 ? ldg_pack<T, VEC>(vl + t.o1) : pack_zero<T, VEC>();
+          const Pack<T, VEC> v2 = t.k2 ? ldg_pack<T, VEC>(vl + t.o2) : pack_zero<T, VEC>();
+          const Pack<T, VEC> v3 = t.k3 ? ldg_pack<T, VEC>(vl + t.o3) : pack_zero<T, VEC>();
+          const Pack<T, VEC> v4 = t.k4 ? ldg_pack<T, VEC>(vl + t.o4) : pack_zero<T, VEC>();
+          Pack<T, VEC> r1, r2, r3, r4;
+#pragma unroll
+          for (int c = 0; c < VEC; ++c) {
+            const T gc = g[i].v[c];
+            s_a += gc * (t.w1 * v1.v[c] + t.w2 * v2.v[c] + t.w3 * v3.v[c] + t.w4 * v4.v[c]);
+            s_x += gc * (hy * (v2.v[c] - v1.v[c]) + t.ly * (v4.v[c] - v3.v[c]));
+            s_y += gc * (hx * (v3.v[c] - v1.v[c]) + t.lx * (v4.v[c] - v2.v[c]));
+            r1.v[c] = a1 * gc;
+            r2.v[c] = a2 * gc;
+            r3.v[c] = a3 * gc;
+            r4.v[c] = a4 * gc;
+          }
+          if (active) {
+            T* gl = gvhead + lofs + co;
+            if (t.k1) red_add_pack<T, VEC>(gl + t.o1, r1);
+            if (t.k2) red_add_pack<T, VEC>(gl + t.o2, r2);
+            if (t.k3) red_add_pack<T, VEC>(gl + t.o3, r3);
+            if (t.k4) red_add_pack<T, VEC>(gl + t.o4, r4);
+          }
+        }
+      }
+      s_a = group_sum<T, G>(s_a);
+      s_x = group_sum<T, G>(s_x);
+      s_y = group_sum<T, G>(s_y);
+      if (active && lane == 0) {
+        gap[0] = s_a;
+        glp[0] = s_x * a * T(W);
+        glp[1] = s_y * a * T(H);
+      }
+      lp += 2;
+      ap += 1;
+      glp += 2;
+      gap += 1;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// Host side: dispatch on (VEC, G, ITERS), launch, error reporting
+// ------------------------------------------------------------------------------------
+struct Dims {
+  int N, S, M, D, L, Lq, P;
+};
+
+static int check_dims(const Dims& d) {
+  if (d.N < 0 || d.Lq < 0 || d.S <= 0 || d.M <= 0 || d.D <= 0 || d.L <= 0 || d.P <= 0)
+    return MSDA_E_DIMS;
+  if (d.L > MSDA_B200_MAX_LEVELS) return MSDA_E_LEVELS;
+  if (int64_t(d.S) * d.M * d.D > int64_t(INT32_MAX)) return MSDA_E_TOO_LARGE;
+  return 0;
+}
+
+template <typename T>
+static bool aligned16(const T* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+#define MSDA_LAUNCH_FWD(VEC_, G_, IT_)                                                       \
+  msda_fwd_kernel<T, VEC_, G_, IT_><<<grid_for(G_), kThreads, 0, st>>>(                      \
+      value, shapes, loc, attn, out, d.S, d.M, d.D, d.L, d.Lq, d.P, groups)
+#define MSDA_LAUNCH_BWD(VEC_, G_, IT_)                                                       \
+  msda_bwd_kernel<T, VEC_, G_, IT_><<<grid_for(G_), kThreads, 0, st>>>(                      \
+      value, shapes, loc, attn, gout, gval, gloc, gattn, d.S, d.M, d.D, d.L, d.Lq, d.P, groups)
+
+// Picks lanes-per-group G and packs-per-lane ITERS for `npacks` 16-byte packs per head.
+static void pick_shape(int npacks, int* G, int* iters) {
+  int g = 1;
+  while (g < 8 && g < npacks) g <<= 1;           // 1,2,4,8
+  if (npacks == 9) g = 4;                        // D=36 fp32: 3 iterations at 75% lane use beats 2 at 56%
+  *G = g;
+  *iters = (npacks + g - 1) / g;
+}
+
+template <typename T>
+static int forward_impl(const T* value, const int64_t* shapes, const T* loc, const T* attn, T* out,
+                        const Dims& d, cudaStream_t st) {
+  if (int rc = check_dims(d)) return rc;
+  if (!value || !shapes || !loc || !attn || !out) return MSDA_E_NULLPTR;
+  const int64_t groups = int64_t(d.N) * d.Lq * d.M;
+  if (groups == 0) return 0;
+  constexpr int V16 = 16 / int(sizeof(T));
+  const bool vec_ok = (d.D % V16 == 0) && aligned16(value) && aligned16(out);
+  auto grid_for = [&](int G) { return unsigned((groups * G + kThreads - 1) / kThreads); };
+  bool launched = false;
+  if constexpr (sizeof(T) == 4) {
+    // staged kernels for the shipped geometry (fp32, 128-byte head rows)
+    const int variant = g_fwd_variant.load(std::memory_order_relaxed);
+    const int LP = d.L * d.P;
+    if (vec_ok && d.D == 32 && LP <= kMaxLP && aligned16(loc) && (variant == MODE_ROWS || variant == MODE_TAPS)) {
+      const unsigned grid = unsigned((groups + kGroupsPerCta - 1) / kGroupsPerCta);
+      const size_t smem = fwd_d32_smem_bytes(variant, LP);
+      if (variant == MODE_ROWS)
+        msda_fwd_d32_kernel<MODE_ROWS><<<grid, kFwdThreads, smem, st>>>(value, shapes, loc, attn, out, d.S, d.M,
+                                                                        d.L, d.Lq, d.P, groups);
+      else
+        msda_fwd_d32_kernel<MODE_TAPS><<<grid, kFwdThreads, smem, st>>>(value, shapes, loc, attn, out, d.S, d.M,
+                                                                        d.L, d.Lq, d.P, groups);
+      launched = true;
+    }
+  }
+  if (!launched && vec_ok) {
+    int G, it;
+    pick_shape(d.D / V16, &G, &it);
+    launched = true;
+    if (G == 8 && it == 1) MSDA_LAUNCH_FWD(V16, 8, 1);
+    else if (G == 8 && it == 2) MSDA_LAUNCH_FWD(V16, 8, 2);
+    else if (G == 8 && it <= 4) MSDA_LAUNCH_FWD(V16, 8, 4);
+    else if (G == 4 && it == 1) MSDA_LAUNCH_FWD(V16, 4, 1);
+    else if (G == 4 && it <= 3) MSDA_LAUNCH_FWD(V16, 4, 3);
+    else if (G == 2) MSDA_LAUNCH_FWD(V16, 2, 2);
+    else if (G == 1) MSDA_LAUNCH_FWD(V16, 1, 1);
+    else launched = false;
+  }
+  if (!launched) {
+    // odd channel counts / unaligned views / very wide heads: scalar lanes, strided channels
+    if (d.D <= 8) MSDA_LAUNCH_FWD(1, 8, 1);
+    else if (d.D <= 32) MSDA_LAUNCH_FWD(1, 8, 4);
+    else if (d.D <= 128) MSDA_LAUNCH_FWD(1, 8, 16);
+    else return MSDA_E_TOO_LARGE;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+
+template <typename T>
+static int backward_impl(const T* value, const int64_t* shapes, const T* loc, const T* attn,
+                         const T* gout, T* gval, T* gloc, T* gattn, const Dims& d, cudaStream_t st) {
+  if (int rc = check_dims(d)) return rc;
+  if (!value || !shapes || !loc || !attn || !gout || !gval || !gloc || !gattn) return MSDA_E_NULLPTR;
+  if (d.N > 0) {
+    cudaError_t e = cudaMemsetAsync(gval, 0, sizeof(T) * size_t(d.N) * d.S * d.M * d.D, st);
+    if (e != cudaSuccess) return int(e);
+  }
+  const int64_t groups = int64_t(d.N) * d.Lq * d.M;
+  if (groups == 0) return 0;
+  constexpr int V16 = 16 / int(sizeof(T));
+  const bool vec_ok = (d.D % V16 == 0) && aligned16(value) && aligned16(gout) && aligned16(gval);
+  auto grid_for = [&](int G) { return unsigned((groups * G + kThreads - 1) / kThreads); };
+  bool launched = false;
+  if (vec_ok) {
+    int G, it;
+    pick_shape(d.D / V16, &G, &it);
+    launched = true;
+    if (G == 8 && it == 1) MSDA_LAUNCH_BWD(V16, 8, 1);
+    else if (G == 8 && it == 2) MSDA_LAUNCH_BWD(V16, 8, 2);
+    else if (G == 8 && it <= 4) MSDA_LAUNCH_BWD(V16, 8, 4);
+    else if (G == 4 && it == 1) MSDA_LAUNCH_BWD(V16, 4, 1);
+    else if (G == 4 && it <= 3) MSDA_LAUNCH_BWD(V16, 4, 3);
+    else if (G == 2) MSDA_LAUNCH_BWD(V16, 2, 2);
+    else if (G == 1) MSDA_LAUNCH_BWD(V16, 1, 1);
+    else launched = false;
+  }
+  if (!launched) {
+    // odd channel counts / unaligned views / very wide heads: scalar lanes, strided channels
+    if (d.D <= 8) MSDA_LAUNCH_BWD(1, 8, 1);
+    else if (d.D <= 32) MSDA_LAUNCH_BWD(1, 8, 4);
+    else if (d.D <= 128) MSDA_LAUNCH_BWD(1, 8, 16);
+    else return MSDA_E_TOO_LARGE;
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+
+// ---- host-buffer convenience path (end-to-end timing, C callers without a CUDA runtime) ---
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+#define MSDA_CUDA_TRY(expr)                   \
+  do {                                        \
+    cudaError_t e__ = (expr);                 \
+    if (e__ != cudaSuccess) return int(e__);  \
+  } while (0)
+
+}  // namespace msda
+
+using namespace msda;
+
+extern "C" {
+
+int msda_b200_abi_version(void) { return MSDA_B200_ABI_VERSION; }
+
+const char* msda_b200_error_string(int code) {
+  switch (code) {
+    case 0: return "success";
+    case MSDA_E_NULLPTR: return "msda_b200: NULL pointer argument";
+    case MSDA_E_DIMS: return "msda_b200: non-positive dimension";
+    case MSDA_E_TOO_LARGE: return "msda_b200: S*M*D exceeds 2^31-1 elements or D unsupported";
+    case MSDA_E_LEVELS: return "msda_b200: too many levels";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString(cudaError_t(code));
+  return "msda_b200: unknown error";
+}
+
+void msda_b200_set_variant(int fwd_variant, int bwd_variant) {
+  g_fwd_variant.store(fwd_variant);
+  g_bwd_variant.store(bwd_variant);
+}
+
+uint64_t msda_b200_launch_count(void) { return g_launches.load(); }
+
+int msda_b200_forward_f32(const float* value, const int64_t* spatial_shapes, const float* sampling_loc,
+                          const float* attn_weight, float* output, int N, int S, int M, int D, int L,
+                          int Lq, int P, void* stream) {
+  return forward_impl<float>(value, spatial_shapes, sampling_loc, attn_weight, output,
+                             Dims{N, S, M, D, L, Lq, P}, cudaStream_t(stream));
+}
+
+int msda_b200_forward_f64(const double* value, const int64_t* spatial_shapes, const double* sampling_loc,
+                          const double* attn_weight, double* output, int N, int S, int M, int D, int L,
+                          int Lq, int P, void* stream) {
+  return forward_impl<double>(value, spatial_shapes, sampling_loc, attn_weight, output,
+                              Dims{N, S, M, D, L, Lq, P}, cudaStream_t(stream));
+}
+
+int msda_b200_backward_f32(const float* value, const int64_t* spatial_shapes, const float* sampling_loc,
+                           const float* attn_weight, const float* grad_output, float* grad_value,
+                           float* grad_sampling_loc, float* grad_attn_weight, int N, int S, int M, int D,
+                           int L, int Lq, int P, void* stream) {
+  return backward_impl<float>(value, spatial_shapes, sampling_loc, attn_weight, grad_output, grad_value,
+                              grad_sampling_loc, grad_attn_weight, Dims{N, S, M, D, L, Lq, P},
+                              cudaStream_t(stream));
+}
+
+int msda_b200_backward_f64(const double* value, const int64_t* spatial_shapes, const double* sampling_loc,
+                           const double* attn_weight, const double* grad_output, double* grad_value,
+                           double* grad_sampling_loc, double* grad_attn_weight, int N, int S, int M, int D,
+                           int L, int Lq, int P, void* stream) {
+  return backward_impl<double>(value, spatial_shapes, sampling_loc, attn_weight, grad_output, grad_value,
+                               grad_sampling_loc, grad_attn_weight, Dims{N, S, M, D, L, Lq, P},
+                               cudaStream_t(stream));
+}
+
+int msda_b200_forward_host_f32(const float* value, const int64_t* spatial_shapes, const float* sampling_loc,
+                               const float* attn_weight, float* output, int N, int S, int M, int D, int L,
+                               int Lq, int P, int device) {
+  const Dims d{N, S, M, D, L, Lq, P};
+  if (int rc = check_dims(d)) return rc;
+  if (!value || !spatial_shapes || !sampling_loc || !attn_weight || !output) return MSDA_E_NULLPTR;
+  MSDA_CUDA_TRY(cudaSetDevice(device));
+  const size_t nv = size_t(N) * S * M * D, ns = size_t(N) * Lq * M * L * P, no = size_t(N) * Lq * M * D;
+  DevBuf dv, dsz, dl, da, dout;
+  MSDA_CUDA_TRY(dv.alloc(nv * 4));
+  MSDA_CUDA_TRY(dsz.alloc(size_t(L) * 16));
+  MSDA_CUDA_TRY(dl.alloc(ns * 8));
+  MSDA_CUDA_TRY(da.alloc(ns * 4));
+  MSDA_CUDA_TRY(dout.alloc(no * 4));
+  cudaStream_t st = nullptr;
+  MSDA_CUDA_TRY(cudaMemcpyAsync(dv.p, value, nv * 4, cudaMemcpyHostToDevice, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(dsz.p, spatial_shapes, size_t(L) * 16, cudaMemcpyHostToDevice, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(dl.p, sampling_loc, ns * 8, cudaMemcpyHostToDevice, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(da.p, attn_weight, ns * 4, cudaMemcpyHostToDevice, st));
+  int rc = forward_impl<float>((const float*)dv.p, (const int64_t*)dsz.p, (const float*)dl.p,
+                               (const float*)da.p, (float*)dout.p, d, st);
+  if (rc) return rc;
+  MSDA_CUDA_TRY(cudaMemcpyAsync(output, dout.p, no * 4, cudaMemcpyDeviceToHost, st));
+  MSDA_CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int msda_b200_backward_host_f32(const float* value, const int64_t* spatial_shapes, const float* sampling_loc,
+                                const float* attn_weight, const float* grad_output, float* grad_value,
+                                float* grad_sampling_loc, float* grad_attn_weight, int N, int S, int M,
+                                int D, int L, int Lq, int P, int device) {
+  const Dims d{N, S, M, D, L, Lq, P};
+  if (int rc = check_dims(d)) return rc;
+  if (!value || !spatial_shapes || !sampling_loc || !attn_weight || !grad_output || !grad_value ||
+      !grad_sampling_loc || !grad_attn_weight)
+    return MSDA_E_NULLPTR;
+  MSDA_CUDA_TRY(cudaSetDevice(device));
+  const size_t nv = size_t(N) * S * M * D, ns = size_t(N) * Lq * M * L * P, no = size_t(N) * Lq * M * D;
+  DevBuf dv, dsz, dl, da, dgo, dgv, dgl, dga;
+  MSDA_CUDA_TRY(dv.alloc(nv * 4));
+  MSDA_CUDA_TRY(dsz.alloc(size_t(L) * 16));
+  MSDA_CUDA_TRY(dl.alloc(ns * 8));
+  MSDA_CUDA_TRY(da.alloc(ns * 4));
+  MSDA_CUDA_TRY(dgo.alloc(no * 4));
+  MSDA_CUDA_TRY(dgv.alloc(nv * 4));
+  MSDA_CUDA_TRY(dgl.alloc(ns * 8));
+  MSDA_CUDA_TRY(dga.alloc(ns * 4));
+  cudaStream_t st = nullptr;
+  MSDA_CUDA_TRY(cudaMemcpyAsync(dv.p, value, nv * 4, cudaMemcpyHostToDevice, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(dsz.p, spatial_shapes, size_t(L) * 16, cudaMemcpyHostToDevice, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(dl.p, sampling_loc, ns * 8, cudaMemcpyHostToDevice, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(da.p, attn_weight, ns * 4, cudaMemcpyHostToDevice, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(dgo.p, grad_output, no * 4, cudaMemcpyHostToDevice, st));
+  int rc = backward_impl<float>((const float*)dv.p, (const int64_t*)dsz.p, (const float*)dl.p,
+                                (const float*)da.p, (const float*)dgo.p, (float*)dgv.p, (float*)dgl.p,
+                                (float*)dga.p, d, st);
+  if (rc) return rc;
+  MSDA_CUDA_TRY(cudaMemcpyAsync(grad_value, dgv.p, nv * 4, cudaMemcpyDeviceToHost, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(grad_sampling_loc, dgl.p, ns * 8, cudaMemcpyDeviceToHost, st));
+  MSDA_CUDA_TRY(cudaMemcpyAsync(grad_attn_weight, dga.p, ns * 4, cudaMemcpyDeviceToHost, st));
+  MSDA_CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,141 @@
+// Python module `MultiScaleDeformableAttention` -- same name and same two entry points as the
+// reference's pybind surface (src/trackformer/models/ops/src/vision.cpp:4-7,
+// src/ms_deform_attn.h:10-50), so `import MultiScaleDeformableAttention as MSDA` in the
+// reference's ops/functions/ms_deform_attn_func.py:11 resolves to this library unchanged.
+//
+// This file is glue only: argument validation, output allocation, current-stream lookup and
+// a call through the C ABI of libmsda_b200 (include/msda_b200.h).  Differences from the
+// reference glue, all deliberate:
+//   * kernel-launch / CUDA errors raise (the reference printf()s them, ms_deform_im2col_cuda.cuh:404-408)
+//   * no `columns` scratch tensor, no at::sum, no per-level ATen ops for level_start_index
+//   * im2col_step is validated exactly like the reference (ms_deform_attn_cuda.cu:46-48) and then
+//     ignored: one launch covers the whole batch
+//   * CPU tensors raise "Not implemented on the CPU" like ms_deform_attn.h:27 -- there is no CPU fallback
+#include <torch/extension.h>
+
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/msda_b200.h"
+
+namespace {
+
+struct Geometry {
+  int N, S, M, D, L, Lq, P;
+};
+
+Geometry validate(const at::Tensor& value, const at::Tensor& spatial_shapes,
+                  const at::Tensor& sampling_loc, const at::Tensor& attn_weight,
+                  int64_t im2col_step) {
+  TORCH_CHECK(value.is_cuda(), "Not implemented on the CPU");
+  TORCH_CHECK(spatial_shapes.is_cuda(), "spatial_shapes must be a CUDA tensor");
+  TORCH_CHECK(sampling_loc.is_cuda(), "sampling_loc must be a CUDA tensor");
+  TORCH_CHECK(attn_weight.is_cuda(), "attn_weight must be a CUDA tensor");
+  TORCH_CHECK(value.is_contiguous(), "value tensor has to be contiguous");
+  TORCH_CHECK(value.scalar_type() == at::kFloat || value.scalar_type() == at::kDouble,
+              "ms_deform_attn: value must be float32 or float64, got ", value.scalar_type());
+  TORCH_CHECK(sampling_loc.scalar_type() == value.scalar_type() &&
+                  attn_weight.scalar_type() == value.scalar_type(),
+              "ms_deform_attn: value, sampling_loc and attn_weight must share one dtype");
+  TORCH_CHECK(spatial_shapes.scalar_type() == at::kLong, "spatial_shapes must be int64");
+  TORCH_CHECK(value.dim() == 4, "value must be [N, S, M, D]");
+  TORCH_CHECK(spatial_shapes.dim() == 2 && spatial_shapes.size(1) == 2, "spatial_shapes must be [L, 2]");
+  TORCH_CHECK(sampling_loc.dim() == 6 && sampling_loc.size(5) == 2,
+              "sampling_loc must be [N, Lq, M, L, P, 2]");
+  TORCH_CHECK(attn_weight.dim() == 5, "attn_weight must be [N, Lq, M, L, P]");
+  Geometry g;
+  g.N = int(value.size(0));
+  g.S = int(value.size(1));
+  g.M = int(value.size(2));
+  g.D = int(value.size(3));
+  g.L = int(spatial_shapes.size(0));
+  g.Lq = int(sampling_loc.size(1));
+  g.P = int(sampling_loc.size(4));
+  TORCH_CHECK(sampling_loc.size(0) == g.N && sampling_loc.size(2) == g.M && sampling_loc.size(3) == g.L,
+              "sampling_loc shape does not match value / spatial_shapes");
+  TORCH_CHECK(attn_weight.size(0) == g.N && attn_weight.size(1) == g.Lq && attn_weight.size(2) == g.M &&
+                  attn_weight.size(3) == g.L && attn_weight.size(4) == g.P,
+              "attn_weight shape does not match sampling_loc");
+  TORCH_CHECK(value.device() == spatial_shapes.device() && value.device() == sampling_loc.device() &&
+                  value.device() == attn_weight.device(),
+              "ms_deform_attn: all tensors must live on the same device");
+  const int64_t step = std::min<int64_t>(g.N, im2col_step);
+  TORCH_CHECK(g.N == 0 || (step > 0 && g.N % step == 0), "batch(", g.N, ") must divide im2col_step(", step, ")");
+  return g;
+}
+
+void raise_on_error(int rc, const char* what) {
+  TORCH_CHECK(rc == 0, what, " failed: ", msda_b200_error_string(rc), " (code ", rc, ")");
+}
+
+}  // namespace
+
+at::Tensor ms_deform_attn_forward(const at::Tensor& value, const at::Tensor& spatial_shapes,
+                                  const at::Tensor& sampling_loc, const at::Tensor& attn_weight,
+                                  const int64_t im2col_step) {
+  const Geometry g = validate(value, spatial_shapes, sampling_loc, attn_weight, im2col_step);
+  const c10::cuda::CUDAGuard guard(value.device());
+  const at::Tensor shapes = spatial_shapes.contiguous();
+  const at::Tensor loc = sampling_loc.contiguous();
+  const at::Tensor attn = attn_weight.contiguous();
+  at::Tensor out = at::empty({g.N, g.Lq, int64_t(g.M) * g.D}, value.options());
+  void* stream = c10::cuda::getCurrentCUDAStream().stream();
+  int rc;
+  if (value.scalar_type() == at::kFloat) {
+    rc = msda_b200_forward_f32(value.data_ptr<float>(), shapes.data_ptr<int64_t>(), loc.data_ptr<float>(),
+                               attn.data_ptr<float>(), out.data_ptr<float>(), g.N, g.S, g.M, g.D, g.L,
+                               g.Lq, g.P, stream);
+  } else {
+    rc = msda_b200_forward_f64(value.data_ptr<double>(), shapes.data_ptr<int64_t>(), loc.data_ptr<double>(),
+                               attn.data_ptr<double>(), out.data_ptr<double>(), g.N, g.S, g.M, g.D, g.L,
+                               g.Lq, g.P, stream);
+  }
+  raise_on_error(rc, "ms_deform_attn_forward");
+  return out;
+}
+
+std::vector<at::Tensor> ms_deform_attn_backward(const at::Tensor& value, const at::Tensor& spatial_shapes,
+                                                const at::Tensor& sampling_loc,
+                                                const at::Tensor& attn_weight,
+                                                const at::Tensor& grad_output, const int64_t im2col_step) {
+  const Geometry g = validate(value, spatial_shapes, sampling_loc, attn_weight, im2col_step);
+  TORCH_CHECK(grad_output.is_cuda(), "grad_output must be a CUDA tensor");
+  TORCH_CHECK(grad_output.scalar_type() == value.scalar_type(), "grad_output dtype mismatch");
+  TORCH_CHECK(grad_output.numel() == int64_t(g.N) * g.Lq * g.M * g.D, "grad_output must be [N, Lq, M*D]");
+  const c10::cuda::CUDAGuard guard(value.device());
+  const at::Tensor shapes = spatial_shapes.contiguous();
+  const at::Tensor loc = sampling_loc.contiguous();
+  const at::Tensor attn = attn_weight.contiguous();
+  const at::Tensor gout = grad_output.contiguous();
+  at::Tensor grad_value = at::empty_like(value);  // zero-filled inside the C-ABI call
+  at::Tensor grad_loc = at::empty_like(loc);
+  at::Tensor grad_attn = at::empty_like(attn);
+  void* stream = c10::cuda::getCurrentCUDAStream().stream();
+  int rc;
+  if (value.scalar_type() == at::kFloat) {
+    rc = msda_b200_backward_f32(value.data_ptr<float>(), shapes.data_ptr<int64_t>(), loc.data_ptr<float>(),
+                                attn.data_ptr<float>(), gout.data_ptr<float>(), grad_value.data_ptr<float>(),
+                                grad_loc.data_ptr<float>(), grad_attn.data_ptr<float>(), g.N, g.S, g.M, g.D,
+                                g.L, g.Lq, g.P, stream);
+  } else {
+    rc = msda_b200_backward_f64(value.data_ptr<double>(), shapes.data_ptr<int64_t>(),
+                                loc.data_ptr<double>(), attn.data_ptr<double>(), gout.data_ptr<double>(),
+                                grad_value.data_ptr<double>(), grad_loc.data_ptr<double>(),
+                                grad_attn.data_ptr<double>(), g.N, g.S, g.M, g.D, g.L, g.Lq, g.P, stream);
+  }
+  raise_on_error(rc, "ms_deform_attn_backward");
+  return {grad_value, grad_loc, grad_attn};
+}
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "B200 (sm_100a) multi-scale deformable attention; drop-in for the reference extension";
+  m.def("ms_deform_attn_forward", &ms_deform_attn_forward, "ms_deform_attn_forward");
+  m.def("ms_deform_attn_backward", &ms_deform_attn_backward, "ms_deform_attn_backward");
+  // extras (not in the reference surface)
+  m.def("abi_version", []() { return msda_b200_abi_version(); });
+  m.def("launch_count", []() { return msda_b200_launch_count(); });
+  m.def("set_variant", [](int f, int b) { msda_b200_set_variant(f, b); });
+}

@@ -1,0 +1,41 @@
+"""Autograd binding of the B200 MSDeformAttn kernels.
+
+Mirror of the reference's ``MSDeformAttnFunction``
+(src/trackformer/models/ops/functions/ms_deform_attn_func.py:14-31): same ``apply`` signature
+``(value, value_spatial_shapes, sampling_locations, attention_weights, im2col_step)``, gradients for
+arguments 0, 2 and 3 only, ``once_differentiable`` backward.  The compiled extension is resolved
+through :mod:`trackformer_b200.ext` -- it must exist; there is no PyTorch fallback here (the
+pure-PyTorch restatement lives in ``oracle/`` and is test infrastructure only).
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ext
+
+
+class MSDeformAttnFunction(Function):
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, sampling_locations, attention_weights, im2col_step):
+        msda = ext.load()
+        ctx.im2col_step = int(im2col_step)
+        out = msda.ms_deform_attn_forward(value, value_spatial_shapes, sampling_locations,
+                                          attention_weights, ctx.im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, sampling_locations, attention_weights)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, loc, attn = ctx.saved_tensors
+        g_value, g_loc, g_attn = ext.load().ms_deform_attn_backward(
+            value, shapes, loc, attn, grad_output.contiguous(), ctx.im2col_step)
+        return g_value, None, g_loc, g_attn, None
+
+
+def ms_deform_attn(value: torch.Tensor, spatial_shapes: torch.Tensor, sampling_locations: torch.Tensor,
+                   attention_weights: torch.Tensor, im2col_step: int = 64) -> torch.Tensor:
+    """Functional form: ``[N,S,M,D] x [L,2] x [N,Lq,M,L,P,2] x [N,Lq,M,L,P] -> [N,Lq,M*D]``."""
+    return MSDeformAttnFunction.apply(value, spatial_shapes, sampling_locations, attention_weights, im2col_step)
