@@ -6,7 +6,7 @@ libmsda_b200.so) or the C ABI directly via ctypes -- and is checked against
   * the golden fixtures recorded from the reference's own function (tests/golden/), and
   * the oracle (plain-C restatement, oracle/msda_oracle.c) on seeded inputs, and
   * at full BASELINE sizes, size-independent properties (linearity, constant fields, adjointness).
-Tolerances: fp32 1e-4 relative / 1e-5 absolute on O(1) data (summation order differs from the
+Tolerances: fp32 1e-4 relative / 1e-4 absolute on O(1) data (summation order differs from the
 reference's at::sum and the backward uses atomics); fp64 1e-10.  The reference's own tests
 accept rtol 1e-2 / atol 1e-3 (ops/test.py:31).
 """
@@ -20,7 +20,7 @@ from conftest import golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
 
-F32 = dict(rtol=1e-4, atol=1e-5)
+F32 = dict(rtol=1e-4, atol=1e-4)     # O(1) data, 16..64-term fp32 dot products with cancellation
 F64 = dict(rtol=1e-10, atol=1e-12)
 
 

@@ -1,0 +1,121 @@
+"""Set-prediction loss of the forward+backward hot path.
+
+Mirror of ``SetCriterion`` (src/trackformer/models/detr.py:139-443) for the losses the Deformable-DETR /
+TrackFormer configs use -- ``labels`` (sigmoid focal or weighted cross-entropy), ``boxes`` (L1 + GIoU) and
+``cardinality`` (logging only) -- applied to the last decoder layer and to every auxiliary layer with its own
+Hungarian matching, normalised by the world-averaged number of boxes (one scalar all-reduce, :399-401).
+Mask losses belong to the segmentation heads, which are outside the hot path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .util import (accuracy, box_cxcywh_to_xyxy, generalized_box_iou, get_world_size,
+                   is_dist_avail_and_initialized, sigmoid_focal_loss)
+
+
+class SetCriterion(nn.Module):
+    def __init__(self, num_classes, matcher, weight_dict, eos_coef, losses, focal_loss, focal_alpha,
+                 focal_gamma, tracking, track_query_false_positive_eos_weight):
+        super().__init__()
+        self.num_classes = num_classes
+        self.matcher = matcher
+        self.weight_dict = weight_dict
+        self.eos_coef = eos_coef
+        self.losses = losses
+        w = torch.ones(num_classes + 1)
+        w[-1] = eos_coef
+        self.register_buffer("empty_weight", w)
+        self.focal_loss = focal_loss
+        self.focal_alpha = focal_alpha
+        self.focal_gamma = focal_gamma
+        self.tracking = tracking
+        self.track_query_false_positive_eos_weight = track_query_false_positive_eos_weight
+
+    # ---- index helpers -----------------------------------------------------------------------
+    @staticmethod
+    def _src_idx(indices):
+        batch = torch.cat([torch.full_like(src, i) for i, (src, _) in enumerate(indices)])
+        return batch, torch.cat([src for src, _ in indices])
+
+    def _target_classes(self, logits, targets, indices):
+        idx = self._src_idx(indices)
+        matched = torch.cat([t["labels"][j] for t, (_, j) in zip(targets, indices)])
+        classes = torch.full(logits.shape[:2], self.num_classes, dtype=torch.int64, device=logits.device)
+        classes[idx] = matched
+        return idx, matched, classes
+
+    # ---- losses ------------------------------------------------------------------------------
+    def loss_labels(self, outputs, targets, indices, _, log=True):
+        logits = outputs["pred_logits"]
+        idx, matched, classes = self._target_classes(logits, targets, indices)
+        ce = F.cross_entropy(logits.transpose(1, 2), classes, weight=self.empty_weight, reduction="none")
+        if self.tracking and self.track_query_false_positive_eos_weight:
+            for i, t in enumerate(targets):
+                if "track_query_boxes" in t:
+                    fp = t["track_queries_fal_pos_mask"]
+                    ce[i, fp] *= 1 / self.eos_coef            # false track queries are not down-weighted ...
+                    classes = classes.clone()
+                    classes[i, fp] = 0                        # ... and count with an object-class weight
+        out = {"loss_ce": ce.sum() / self.empty_weight[classes].sum()}
+        if log:
+            out["class_error"] = 100 - accuracy(logits[idx], matched)[0]
+        return out
+
+    def loss_labels_focal(self, outputs, targets, indices, num_boxes, log=True):
+        logits = outputs["pred_logits"]
+        idx, matched, classes = self._target_classes(logits, targets, indices)
+        onehot = torch.zeros([logits.shape[0], logits.shape[1], logits.shape[2] + 1], dtype=logits.dtype,
+                             device=logits.device)
+        onehot.scatter_(2, classes.unsqueeze(-1), 1)
+        loss = sigmoid_focal_loss(logits, onehot[:, :, :-1], num_boxes, alpha=self.focal_alpha,
+                                  gamma=self.focal_gamma) * logits.shape[1]
+        out = {"loss_ce": loss}
+        if log:
+            out["class_error"] = 100 - accuracy(logits[idx], matched)[0]
+        return out
+
+    @torch.no_grad()
+    def loss_cardinality(self, outputs, targets, indices, num_boxes):
+        logits = outputs["pred_logits"]
+        n_gt = torch.as_tensor([len(t["labels"]) for t in targets], device=logits.device)
+        n_pred = (logits.argmax(-1) != logits.shape[-1] - 1).sum(1)
+        return {"cardinality_error": F.l1_loss(n_pred.float(), n_gt.float())}
+
+    def loss_boxes(self, outputs, targets, indices, num_boxes):
+        idx = self._src_idx(indices)
+        src = outputs["pred_boxes"][idx]
+        tgt = torch.cat([t["boxes"][i] for t, (_, i) in zip(targets, indices)], dim=0)
+        l1 = F.l1_loss(src, tgt, reduction="none")
+        giou = 1 - torch.diag(generalized_box_iou(box_cxcywh_to_xyxy(src), box_cxcywh_to_xyxy(tgt)))
+        return {"loss_bbox": l1.sum() / num_boxes, "loss_giou": giou.sum() / num_boxes}
+
+    def get_loss(self, loss, outputs, targets, indices, num_boxes, **kwargs):
+        table = {"labels": self.loss_labels_focal if self.focal_loss else self.loss_labels,
+                 "cardinality": self.loss_cardinality, "boxes": self.loss_boxes}
+        assert loss in table, f"do you really want to compute {loss} loss?"
+        return table[loss](outputs, targets, indices, num_boxes, **kwargs)
+
+    def forward(self, outputs, targets):
+        last = {k: v for k, v in outputs.items() if k != "aux_outputs"}
+        indices = self.matcher(last, targets)
+        num_boxes = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float,
+                                    device=next(iter(outputs.values())).device)
+        if is_dist_avail_and_initialized():
+            torch.distributed.all_reduce(num_boxes)
+        num_boxes = torch.clamp(num_boxes / get_world_size(), min=1).item()
+
+        losses = {}
+        for name in self.losses:
+            losses.update(self.get_loss(name, outputs, targets, indices, num_boxes))
+        for i, aux in enumerate(outputs.get("aux_outputs", ())):
+            aux_indices = self.matcher(aux, targets)
+            for name in self.losses:
+                if name == "masks":
+                    continue
+                kw = {"log": False} if name == "labels" else {}
+                part = self.get_loss(name, aux, targets, aux_indices, num_boxes, **kw)
+                losses.update({f"{k}_{i}": v for k, v in part.items()})
+        return losses

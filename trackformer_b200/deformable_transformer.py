@@ -1,0 +1,279 @@
+"""Deformable transformer (6 encoder + 6 decoder layers) on the B200 MSDeformAttn kernels.
+
+Mirror of src/trackformer/models/deformable_transformer.py (one-stage path, which is what every shipped
+config uses -- cfgs/train_deformable.yaml sets ``with_box_refine: true`` and leaves ``two_stage: false``):
+
+  DeformableTransformer.forward(srcs, masks, pos_embeds, query_embed, targets)       :133-255
+  encoder layer / encoder (+ reference-point grid)                                    :258-327
+  decoder layer / decoder (+ iterative box refinement, detached)                      :330-431
+  track-query concatenation [prev hs_embed ; query tgt], zero query_pos for tracks    :202-225
+  separate prev/current-frame encoder passes for multi-frame attention                :160-173
+
+Module and parameter names equal the reference's, so ``state_dict`` round-trips.  Two-stage proposal
+generation (:77-122,:180-194) is not on the hot path of any shipped configuration and is not built.
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .msda_module import MSDeformAttn
+from .util import inverse_sigmoid
+
+
+def _clones(module: nn.Module, n: int) -> nn.ModuleList:
+    return nn.ModuleList([copy.deepcopy(module) for _ in range(n)])
+
+
+def _activation(name: str):
+    try:
+        return {"relu": F.relu, "gelu": F.gelu, "glu": F.glu}[name]
+    except KeyError:
+        raise RuntimeError(f"activation should be relu/gelu, not {name}.") from None
+
+
+def _add_pos(x, pos):
+    return x if pos is None else x + pos
+
+
+class DeformableTransformerEncoderLayer(nn.Module):
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8,
+                 n_points=4):
+        super().__init__()
+        self.self_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.activation = _activation(activation)
+        self.dropout2 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout3 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+
+    with_pos_embed = staticmethod(_add_pos)
+
+    def forward_ffn(self, src):
+        ff = self.linear2(self.dropout2(self.activation(self.linear1(src))))
+        return self.norm2(src + self.dropout3(ff))
+
+    def forward(self, src, pos, reference_points, spatial_shapes, padding_mask=None):
+        attn = self.self_attn(_add_pos(src, pos), reference_points, src, spatial_shapes, padding_mask)
+        src = self.norm1(src + self.dropout1(attn))
+        return self.forward_ffn(src)
+
+
+class DeformableTransformerEncoder(nn.Module):
+    def __init__(self, encoder_layer, num_layers):
+        super().__init__()
+        self.layers = _clones(encoder_layer, num_layers)
+        self.num_layers = num_layers
+
+    @staticmethod
+    def get_reference_points(spatial_shapes, valid_ratios, device):
+        """Pixel centres of every level, normalised by the valid extent, then expressed in every level's
+        frame: [N, S, L, 2] (deformable_transformer.py:306-319)."""
+        hw = getattr(spatial_shapes, "_hw_list", None) or [(int(h), int(w)) for h, w in spatial_shapes.tolist()]
+        per_level = []
+        for lvl, (h, w) in enumerate(hw):
+            ys = torch.linspace(0.5, h - 0.5, h, dtype=torch.float32, device=device)
+            xs = torch.linspace(0.5, w - 0.5, w, dtype=torch.float32, device=device)
+            gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+            ry = gy.reshape(-1)[None] / (valid_ratios[:, None, lvl, 1] * h)
+            rx = gx.reshape(-1)[None] / (valid_ratios[:, None, lvl, 0] * w)
+            per_level.append(torch.stack((rx, ry), -1))
+        ref = torch.cat(per_level, 1)
+        return ref[:, :, None] * valid_ratios[:, None]
+
+    def forward(self, src, spatial_shapes, valid_ratios, pos=None, padding_mask=None):
+        ref = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device)
+        out = src
+        for layer in self.layers:
+            out = layer(out, pos, ref, spatial_shapes, padding_mask)
+        return out
+
+
+class DeformableTransformerDecoderLayer(nn.Module):
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8,
+                 n_points=4):
+        super().__init__()
+        self.cross_attn = MSDeformAttn(d_model, n_levels, n_heads, n_points)
+        self.dropout1 = nn.Dropout(dropout)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.self_attn = nn.MultiheadAttention(d_model, n_heads, dropout=dropout)
+        self.dropout2 = nn.Dropout(dropout)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.linear1 = nn.Linear(d_model, d_ffn)
+        self.activation = _activation(activation)
+        self.dropout3 = nn.Dropout(dropout)
+        self.linear2 = nn.Linear(d_ffn, d_model)
+        self.dropout4 = nn.Dropout(dropout)
+        self.norm3 = nn.LayerNorm(d_model)
+
+    with_pos_embed = staticmethod(_add_pos)
+
+    def forward_ffn(self, tgt):
+        ff = self.linear2(self.dropout3(self.activation(self.linear1(tgt))))
+        return self.norm3(tgt + self.dropout4(ff))
+
+    def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, src_padding_mask=None,
+                query_attn_mask=None):
+        # query self-attention (dense, tiny: Lq <= ~800) -- sequence-first nn.MultiheadAttention like the reference
+        qk = _add_pos(tgt, query_pos).transpose(0, 1)
+        sa = self.self_attn(qk, qk, tgt.transpose(0, 1), key_padding_mask=query_attn_mask)[0].transpose(0, 1)
+        tgt = self.norm2(tgt + self.dropout2(sa))
+        # deformable cross-attention into the encoder memory
+        ca = self.cross_attn(_add_pos(tgt, query_pos), reference_points, src, src_spatial_shapes,
+                             src_padding_mask, query_attn_mask)
+        tgt = self.norm1(tgt + self.dropout1(ca))
+        return self.forward_ffn(tgt)
+
+
+class DeformableTransformerDecoder(nn.Module):
+    def __init__(self, decoder_layer, num_layers, return_intermediate=False):
+        super().__init__()
+        self.layers = _clones(decoder_layer, num_layers)
+        self.num_layers = num_layers
+        self.return_intermediate = return_intermediate
+        self.bbox_embed = None     # set by DeformableDETR for iterative box refinement
+        self.class_embed = None
+
+    def forward(self, tgt, reference_points, src, src_spatial_shapes, src_valid_ratios, query_pos=None,
+                src_padding_mask=None, query_attn_mask=None):
+        out = tgt
+        hs, refs = [], []
+        for lid, layer in enumerate(self.layers):
+            if reference_points.shape[-1] == 4:
+                ref_in = reference_points[:, :, None] * torch.cat([src_valid_ratios, src_valid_ratios], -1)[:, None]
+            else:
+                assert reference_points.shape[-1] == 2
+                ref_in = reference_points[:, :, None] * src_valid_ratios[:, None]
+            out = layer(out, query_pos, ref_in, src, src_spatial_shapes, src_padding_mask, query_attn_mask)
+
+            if self.bbox_embed is not None:     # refine the reference boxes for the next layer; no gradient through them
+                delta = self.bbox_embed[lid](out)
+                if reference_points.shape[-1] == 4:
+                    refined = delta + inverse_sigmoid(reference_points)
+                else:
+                    refined = torch.cat([delta[..., :2] + inverse_sigmoid(reference_points), delta[..., 2:]], -1)
+                reference_points = refined.sigmoid().detach()
+
+            if self.return_intermediate:
+                hs.append(out)
+                refs.append(reference_points)
+        if self.return_intermediate:
+            return torch.stack(hs), torch.stack(refs)
+        return out, reference_points
+
+
+class DeformableTransformer(nn.Module):
+    def __init__(self, d_model=256, nhead=8, num_encoder_layers=6, num_decoder_layers=6, dim_feedforward=1024,
+                 dropout=0.1, activation="relu", return_intermediate_dec=False, num_feature_levels=4,
+                 dec_n_points=4, enc_n_points=4, two_stage=False, two_stage_num_proposals=300,
+                 multi_frame_attention_separate_encoder=False):
+        super().__init__()
+        if two_stage:
+            raise NotImplementedError("two-stage Deformable-DETR is outside the hot path (no shipped config uses it)")
+        self.d_model = d_model
+        self.nhead = nhead
+        self.two_stage = two_stage
+        self.two_stage_num_proposals = two_stage_num_proposals
+        self.num_feature_levels = num_feature_levels
+        self.multi_frame_attention_separate_encoder = multi_frame_attention_separate_encoder
+
+        enc_levels = num_feature_levels // 2 if multi_frame_attention_separate_encoder else num_feature_levels
+        self.encoder = DeformableTransformerEncoder(
+            DeformableTransformerEncoderLayer(d_model, dim_feedforward, dropout, activation, enc_levels, nhead,
+                                              enc_n_points), num_encoder_layers)
+        self.decoder = DeformableTransformerDecoder(
+            DeformableTransformerDecoderLayer(d_model, dim_feedforward, dropout, activation, num_feature_levels,
+                                              nhead, dec_n_points), num_decoder_layers, return_intermediate_dec)
+        self.level_embed = nn.Parameter(torch.Tensor(num_feature_levels, d_model))
+        self.reference_points = nn.Linear(d_model, 2)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+        for mod in self.modules():
+            if isinstance(mod, MSDeformAttn):
+                mod._reset_parameters()
+        nn.init.xavier_uniform_(self.reference_points.weight, gain=1.0)
+        nn.init.zeros_(self.reference_points.bias)
+        nn.init.normal_(self.level_embed)
+
+    @staticmethod
+    def get_valid_ratio(mask):
+        """Fraction of each padded level that holds image content, as (w, h)."""
+        _, h, w = mask.shape
+        if getattr(mask, "_no_padding", False):
+            return torch.ones(mask.shape[0], 2, dtype=torch.float32, device=mask.device)
+        vh = (~mask[:, :, 0]).sum(1).float() / h
+        vw = (~mask[:, 0, :]).sum(1).float() / w
+        return torch.stack([vw, vh], -1)
+
+    def forward(self, srcs, masks, pos_embeds, query_embed=None, targets=None):
+        assert query_embed is not None
+        hw, src_l, mask_l, pos_l = [], [], [], []
+        for lvl, (src, mask, pos) in enumerate(zip(srcs, masks, pos_embeds)):
+            hw.append((int(src.shape[2]), int(src.shape[3])))
+            src_l.append(src.flatten(2).transpose(1, 2))
+            mask_l.append(mask.flatten(1))
+            pos_l.append(pos.flatten(2).transpose(1, 2) + self.level_embed[lvl].view(1, 1, -1))
+        src_flat = torch.cat(src_l, 1)
+        mask_flat = torch.cat(mask_l, 1)
+        pos_flat = torch.cat(pos_l, 1)
+        spatial_shapes = torch.as_tensor(hw, dtype=torch.long, device=src_flat.device)
+        spatial_shapes._hw_list = hw                     # host copy: lets callees skip device syncs
+        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
+        dense = all(getattr(m, "_no_padding", False) for m in masks)
+        enc_mask = None if dense else mask_flat          # an all-False mask is a no-op in MSDeformAttn
+
+        if self.multi_frame_attention_separate_encoder:
+            half_s, half_l = src_flat.shape[1] // 2, self.num_feature_levels // 2
+
+            def _enc(sl_s, sl_l):
+                shp = spatial_shapes[sl_l]
+                shp._hw_list = hw[sl_l]
+                return self.encoder(src_flat[:, sl_s], shp, valid_ratios[:, sl_l], pos_flat[:, sl_s],
+                                    None if enc_mask is None else enc_mask[:, sl_s])
+            prev_memory = _enc(slice(None, half_s), slice(None, half_l))
+            memory = _enc(slice(half_s, None), slice(half_l, None))
+            memory = torch.cat([memory, prev_memory], 1)
+        else:
+            memory = self.encoder(src_flat, spatial_shapes, valid_ratios, pos_flat, enc_mask)
+
+        bs, _, c = memory.shape
+        query_pos, tgt = torch.split(query_embed, c, dim=1)
+        query_pos = query_pos.unsqueeze(0).expand(bs, -1, -1)
+        tgt = tgt.unsqueeze(0).expand(bs, -1, -1)
+        reference_points = self.reference_points(query_pos).sigmoid()
+
+        if targets is not None and "track_query_hs_embeds" in targets[0]:
+            # track queries: previous-frame output embeddings as content, zero positional part, previous box
+            # centres as reference points; they are prepended to the object queries
+            prev_hs = torch.stack([t["track_query_hs_embeds"] for t in targets])
+            prev_boxes = torch.stack([t["track_query_boxes"] for t in targets])
+            query_pos = torch.cat([torch.zeros_like(prev_hs), query_pos], dim=1)
+            tgt = torch.cat([prev_hs, tgt], dim=1)
+            reference_points = torch.cat([prev_boxes[..., :2], reference_points], dim=1)
+        init_reference = reference_points
+
+        hs, inter_references = self.decoder(tgt, reference_points, memory, spatial_shapes, valid_ratios,
+                                            query_pos, enc_mask, None)
+        return hs, memory, init_reference, inter_references, None, None
+
+
+def build_deforamble_transformer(args):
+    """(sic) -- the reference spells it this way, models/__init__.py:7."""
+    levels = args.num_feature_levels * (2 if args.multi_frame_attention else 1)
+    return DeformableTransformer(
+        d_model=args.hidden_dim, nhead=args.nheads, num_encoder_layers=args.enc_layers,
+        num_decoder_layers=args.dec_layers, dim_feedforward=args.dim_feedforward, dropout=args.dropout,
+        activation="relu", return_intermediate_dec=True, num_feature_levels=levels,
+        dec_n_points=args.dec_n_points, enc_n_points=args.enc_n_points, two_stage=args.two_stage,
+        two_stage_num_proposals=args.num_queries,
+        multi_frame_attention_separate_encoder=args.multi_frame_attention and args.multi_frame_attention_separate_encoder)

@@ -1,0 +1,76 @@
+"""Hungarian matcher between predictions and ground-truth boxes.
+
+Mirror of src/trackformer/models/matcher.py:13-141.  The cost matrix (focal / softmax class cost, L1 box
+cost, GIoU cost) is built on the GPU; the linear-sum-assignment itself runs on the host with scipy exactly
+like the reference (:104,:127) -- the index bookkeeping downstream must stay bit-exact, so the solver is not
+swapped.  Track-query forcing (:108-125): false-positive track queries can match nothing, every other track
+query is pinned to the ground-truth box of its identity.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from scipy.optimize import linear_sum_assignment
+from torch import nn
+
+from .util import box_cxcywh_to_xyxy, generalized_box_iou
+
+
+class HungarianMatcher(nn.Module):
+    def __init__(self, cost_class: float = 1, cost_bbox: float = 1, cost_giou: float = 1,
+                 focal_loss: bool = False, focal_alpha: float = 0.25, focal_gamma: float = 2.0):
+        super().__init__()
+        assert cost_class != 0 or cost_bbox != 0 or cost_giou != 0, "all costs cant be 0"
+        self.cost_class = cost_class
+        self.cost_bbox = cost_bbox
+        self.cost_giou = cost_giou
+        self.focal_loss = focal_loss
+        self.focal_alpha = focal_alpha
+        self.focal_gamma = focal_gamma
+
+    @torch.no_grad()
+    def forward(self, outputs, targets):
+        bs, nq = outputs["pred_logits"].shape[:2]
+        logits = outputs["pred_logits"].flatten(0, 1)
+        boxes = outputs["pred_boxes"].flatten(0, 1)
+        tgt_ids = torch.cat([t["labels"] for t in targets])
+        tgt_boxes = torch.cat([t["boxes"] for t in targets])
+
+        if self.focal_loss:
+            p = logits.sigmoid()
+            neg = (1 - self.focal_alpha) * (p ** self.focal_gamma) * (-(1 - p + 1e-8).log())
+            pos = self.focal_alpha * ((1 - p) ** self.focal_gamma) * (-(p + 1e-8).log())
+            c_class = pos[:, tgt_ids] - neg[:, tgt_ids]
+        else:
+            c_class = -logits.softmax(-1)[:, tgt_ids]
+        c_bbox = torch.cdist(boxes, tgt_boxes, p=1)
+        c_giou = -generalized_box_iou(box_cxcywh_to_xyxy(boxes), box_cxcywh_to_xyxy(tgt_boxes))
+        cost = self.cost_bbox * c_bbox + self.cost_class * c_class + self.cost_giou * c_giou
+        cost = cost.view(bs, nq, -1).cpu()
+
+        sizes = [len(t["boxes"]) for t in targets]
+        for i, t in enumerate(targets):
+            if "track_query_match_ids" not in t:
+                continue
+            col0 = sum(sizes[:i])
+            fal_pos = t["track_queries_fal_pos_mask"].tolist()
+            is_track = t["track_queries_mask"].tolist()
+            match_ids = t["track_query_match_ids"].tolist()
+            k = 0
+            for j in range(cost.shape[1]):
+                if fal_pos[j]:
+                    cost[i, j] = np.inf
+                elif is_track[j]:
+                    col = match_ids[k] + col0
+                    k += 1
+                    cost[i, j] = np.inf
+                    cost[i, :, col] = np.inf
+                    cost[i, j, col] = -1
+        picks = [linear_sum_assignment(c[i]) for i, c in enumerate(cost.split(sizes, -1))]
+        return [(torch.as_tensor(r, dtype=torch.int64), torch.as_tensor(c, dtype=torch.int64)) for r, c in picks]
+
+
+def build_matcher(args):
+    return HungarianMatcher(cost_class=args.set_cost_class, cost_bbox=args.set_cost_bbox,
+                            cost_giou=args.set_cost_giou, focal_loss=args.focal_loss,
+                            focal_alpha=args.focal_alpha, focal_gamma=args.focal_gamma)

@@ -1,0 +1,99 @@
+"""``MSDeformAttn`` -- the multi-scale deformable attention layer on the B200 kernels.
+
+Mirror of the reference module (src/trackformer/models/ops/modules/ms_deform_attn.py:15-89):
+same constructor, same sub-module names (``sampling_offsets``, ``attention_weights``, ``value_proj``,
+``output_proj`` -- checkpoints and the name-based optimiser groups of src/train.py:101-110 keep
+working), same ``forward`` signature and the same arithmetic, including the reference's
+normalisation of the (x, y) offsets by ``input_spatial_shapes`` as stored, i.e. (H, W)
+(ms_deform_attn.py:78-79).
+
+Host-side differences (results identical up to fp32 rounding):
+  * the two query projections (offsets: 2*M*L*P outputs, weights: M*L*P outputs) run as ONE GEMM over
+    the concatenated weight -- one pass over ``query`` instead of two;
+  * the core op is :class:`trackformer_b200.msda_function.MSDeformAttnFunction` (CUDA only, no fallback).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from .msda_function import MSDeformAttnFunction
+
+# the 8 compass directions the reference seeds the per-head offset bias with (ms_deform_attn.py:36)
+_COMPASS = ((-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 1), (1, -1), (1, 0), (1, 1))
+
+
+class MSDeformAttn(nn.Module):
+    def __init__(self, d_model: int = 256, n_levels: int = 4, n_heads: int = 8, n_points: int = 4,
+                 im2col_step: int = 64):
+        super().__init__()
+        if d_model % n_heads != 0:
+            raise AssertionError("d_model must be divisible by n_heads")
+        self.im2col_step = im2col_step
+        self.d_model = d_model
+        self.n_levels = n_levels
+        self.n_heads = n_heads
+        self.n_points = n_points
+
+        self.sampling_offsets = nn.Linear(d_model, n_heads * n_levels * n_points * 2)
+        self.attention_weights = nn.Linear(d_model, n_heads * n_levels * n_points)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        """Reference init (ms_deform_attn.py:33-47): zero offset weights, compass-grid offset bias scaled
+        by the point index, zero attention logits, xavier value/output projections."""
+        nn.init.zeros_(self.sampling_offsets.weight)
+        compass = torch.tensor(_COMPASS, dtype=torch.float32)                 # the reference hard-codes 8 heads
+        grid = compass.view(self.n_heads, 1, 1, 2).repeat(1, self.n_levels, self.n_points, 1)
+        grid = grid * torch.arange(1, self.n_points + 1, dtype=torch.float32).view(1, 1, -1, 1)
+        with torch.no_grad():
+            self.sampling_offsets.bias = nn.Parameter(grid.reshape(-1))
+        nn.init.zeros_(self.attention_weights.weight)
+        nn.init.zeros_(self.attention_weights.bias)
+        nn.init.xavier_uniform_(self.value_proj.weight)
+        nn.init.zeros_(self.value_proj.bias)
+        nn.init.xavier_uniform_(self.output_proj.weight)
+        nn.init.zeros_(self.output_proj.bias)
+
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes,
+                input_padding_mask=None, query_attn_mask=None):
+        """query [N,Lq,C]; reference_points [N,Lq,L,2|4] in [0,1] over the padded extent;
+        input_flatten [N,S,C]; input_spatial_shapes [L,2]=(H,W) int64; input_padding_mask [N,S] True=pad.
+        Returns [N,Lq,C]."""
+        n, len_q, _ = query.shape
+        _, len_in, _ = input_flatten.shape
+        m, lv, pt = self.n_heads, self.n_levels, self.n_points
+        assert int((input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum()) == len_in
+
+        value = self.value_proj(input_flatten)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None], 0.0)
+        value = value.view(n, len_in, m, self.d_model // m)
+
+        # one GEMM for [offsets | logits]
+        n_off = m * lv * pt * 2
+        w_cat = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
+        b_cat = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
+        proj = F.linear(query, w_cat, b_cat)
+        offsets = proj[..., :n_off].reshape(n, len_q, m, lv, pt, 2)
+        attn = F.softmax(proj[..., n_off:].reshape(n, len_q, m, lv * pt), -1).view(n, len_q, m, lv, pt)
+        if query_attn_mask is not None:
+            attn = attn.masked_fill(query_attn_mask[..., None, None, None], 0.0)
+
+        if reference_points.shape[-1] == 2:
+            locations = reference_points[:, :, None, :, None, :] \
+                + offsets / input_spatial_shapes[None, None, None, :, None, :]
+        elif reference_points.shape[-1] == 4:
+            locations = reference_points[:, :, None, :, None, :2] \
+                + offsets / pt * reference_points[:, :, None, :, None, 2:] * 0.5
+        else:
+            raise ValueError(
+                "Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
+
+        out = MSDeformAttnFunction.apply(value, input_spatial_shapes, locations, attn, self.im2col_step)
+        return self.output_proj(out)
