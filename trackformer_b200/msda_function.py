@@ -15,14 +15,38 @@ from torch.autograd.function import once_differentiable
 
 from . import ext
 
+# Optional per-launch timing (bench.py's roofline leg): when a list is installed here, every forward /
+# backward call is bracketed by CUDA events recorded on the launching stream and appended as
+# (kind, (N, S, M, D, L, Lq, P), start_event, end_event).  None (default) = no events, no overhead.
+_TIMING_SINK = None
+
+
+def set_timing_sink(sink):
+    """Install (or remove, with None) the list that receives per-launch CUDA-event records."""
+    global _TIMING_SINK
+    _TIMING_SINK = sink
+
+
+def _dims(value, loc):
+    n, s, m, d = value.shape
+    _, lq, _, l, p, _ = loc.shape
+    return (n, s, m, d, l, lq, p)
+
 
 class MSDeformAttnFunction(Function):
     @staticmethod
     def forward(ctx, value, value_spatial_shapes, sampling_locations, attention_weights, im2col_step):
         msda = ext.load()
         ctx.im2col_step = int(im2col_step)
+        sink = _TIMING_SINK
+        if sink is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         out = msda.ms_deform_attn_forward(value, value_spatial_shapes, sampling_locations,
                                           attention_weights, ctx.im2col_step)
+        if sink is not None:
+            e1.record()
+            sink.append(("fwd", _dims(value, sampling_locations), e0, e1))
         ctx.save_for_backward(value, value_spatial_shapes, sampling_locations, attention_weights)
         return out
 
@@ -30,8 +54,15 @@ class MSDeformAttnFunction(Function):
     @once_differentiable
     def backward(ctx, grad_output):
         value, shapes, loc, attn = ctx.saved_tensors
+        sink = _TIMING_SINK
+        if sink is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         g_value, g_loc, g_attn = ext.load().ms_deform_attn_backward(
             value, shapes, loc, attn, grad_output.contiguous(), ctx.im2col_step)
+        if sink is not None:
+            e1.record()
+            sink.append(("bwd", _dims(value, loc), e0, e1))
         return g_value, None, g_loc, g_attn, None
 
 
