@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=1)
     ap.add_argument("--no-tf32", action="store_true", help="strict fp32 GEMMs/convs (default: TF32 tensor cores)")
     ap.add_argument("--no-optimizer", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="eager step instead of CUDA-graph replay")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
     args = ap.parse_args()
@@ -212,36 +213,23 @@ def main():
 
     from trackformer_b200 import ext, msda_function
     from trackformer_b200.model_factory import build_model, default_args
+    from trackformer_b200.train_step import TrainStep
     msda = ext.load()          # raises if the sm_100a extension is missing
 
-    torch.manual_seed(0)
+    torch.manual_seed(0)       # same seed on every rank -> identical replicas
     model, criterion, _ = build_model(default_args(device=str(dev)))
     model.to(dev).train()
     criterion.to(dev).train()
-    net = model
-    if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local_rank], gradient_as_bucket_view=True,
-                                                        find_unused_parameters=False)
-    params = [p for p in model.parameters() if p.requires_grad]
-    opt = None if args.no_optimizer else torch.optim.AdamW(params, lr=2e-4, weight_decay=1e-4, fused=True)
-    wd = criterion.weight_dict
 
     g = torch.Generator().manual_seed(1 + rank)
     host_frames = torch.randn(bpg, 3, H, W, generator=g).pin_memory()
     dev_frames = host_frames.to(dev)
     targets = make_targets(bpg, dev, 2 + rank)
 
-    def step(frames):
-        out, tg, _, _, _ = net(frames, targets)
-        losses = criterion(out, tg)
-        loss = sum(losses[k] * wd[k] for k in losses if k in wd)
-        for p in params:
-            p.grad = None
-        loss.backward()
-        if opt is not None:
-            torch.nn.utils.clip_grad_norm_(params, 0.1)
-            opt.step()
-        return loss
+    opt_factory = None if args.no_optimizer else (
+        lambda ps: torch.optim.AdamW(ps, lr=2e-4, weight_decay=1e-4, fused=True))
+    step = TrainStep(model, criterion, opt_factory, max_norm=0.1, use_graphs=not args.no_graphs,
+                     example_frames=dev_frames)
 
     def barrier():
         if world > 1:
@@ -261,30 +249,42 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(max(args.warmup, 3)):
-        step(dev_frames)
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        step(dev_frames, targets)
 
-    # (1) device-resident throughput, per-launch MSDeformAttn timing on the launching stream
-    sink = []
-    msda_function.set_timing_sink(sink)
+    # (1) device-resident throughput
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    launches0 = msda.launch_count()
-    ms_total = timed(lambda: step(dev_frames), args.steps)
-    launches = msda.launch_count() - launches0
+    ms_total = timed(lambda: step(dev_frames, targets), args.steps)
     clocks = sampler.stop() if sampler else None
-    msda_function.set_timing_sink(None)
     value = bpg * world * args.steps / (ms_total / 1e3)
 
     # (2) end to end: pinned host frame -> device every step, loss read back every step
     def e2e_step():
         frames = host_frames.to(dev, non_blocking=True)
-        loss = step(frames)
-        return float(loss.item())
+        return float(step(frames, targets).item())
     e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = bpg * world * args.steps / (ms_e2e / 1e3)
+
+    # (3) per-launch timing of the own kernels.  CUDA-graph replays cannot host per-kernel events, so the same
+    #     step (same model, same inputs, same kernels) is replayed eagerly with every MSDeformAttn launch bracketed
+    #     by CUDA events on the launching stream; the launch counter gives the kernels per step.
+    probe = TrainStep(model, criterion, None, use_graphs=False)
+    probe(dev_frames, targets)
+    sink = []
+    msda_function.set_timing_sink(sink)
+    launches0 = msda.launch_count()
+    probe_steps = min(args.steps, 5)
+    torch.cuda.synchronize(dev)
+    for _ in range(probe_steps):
+        probe(dev_frames, targets)
+    torch.cuda.synchronize(dev)
+    launches_per_step = (msda.launch_count() - launches0) // probe_steps
+    msda_function.set_timing_sink(None)
+    launches = launches_per_step * args.steps
 
     if rank != 0:
         if world > 1:
@@ -302,7 +302,7 @@ def main():
         mean_us = sum(us) / len(us)
         nbytes = msda_alg_bytes(kind, dims)
         per_kernel.append({"kernel": f"msda_{kind}_{role}", "dims_N_S_M_D_L_Lq_P": list(dims), "launches": len(us),
-                           "mean_us": round(mean_us, 2), "total_ms_per_step": round(sum(us) / 1e3 / args.steps, 4),
+                           "mean_us": round(mean_us, 2), "total_ms_per_step": round(sum(us) / 1e3 / probe_steps, 4),
                            "alg_bytes": nbytes, "achieved_gbs": round(nbytes / mean_us / 1e3, 1),
                            "frac": round(nbytes / mean_us / 1e3 / peak, 4)})
     per_kernel.sort(key=lambda r: -r["total_ms_per_step"])
@@ -316,8 +316,9 @@ def main():
         roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak,
                     "unit": "GB/s", "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
                     "mean_launch_us": dom["mean_us"], "alg_bytes_per_launch": dom["alg_bytes"],
-                    "note": "algorithmic (compulsory) bytes / CUDA-event launch time inside the timed step; "
-                            "the gather itself is served by L1/L2, see DESIGN.md"}
+                    "note": "algorithmic (compulsory) bytes / CUDA-event launch time, every launch bracketed by events in an "
+                            "eager replay of the timed step (graph replays cannot host per-kernel events); "
+                            "the gather itself is L1-wavefront bound, see DESIGN.md"}
     msda_ms = sum(r["total_ms_per_step"] for r in per_kernel)
 
     cpu_baseline = None
@@ -333,13 +334,18 @@ def main():
 
     line = {
         "metric": "frames/sec Deformable-DETR R50 800x1333 fwd+bwd", "value": value, "unit": "frames/s",
-        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+        "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "global_batch": bpg * world, "parallelism": f"dp{world}",
                    "dense_math": "TF32 tensor cores (cuDNN/cuBLAS), fp32 accumulate" if tf32 else "strict fp32",
                    "msda_math": "fp32 (hand-written sm_100a kernels)", "dropout": 0.1,
-                   "optimizer": "none" if opt is None else "AdamW(fused) + clip_grad_norm 0.1",
+                   "optimizer": "none" if args.no_optimizer else "AdamW(fused) + clip_grad_norm 0.1",
+                   "execution": "eager" if args.no_graphs else
+                   "model forward + backward replayed from CUDA graphs; Hungarian matching (scipy, host) and the loss "
+                   "run between the two graphs; flat-buffer gradient all-reduce (NCCL) after the backward graph",
+                   "gpu_launches_note": f"{launches_per_step} own kernel launches per step "
+                                        "(12 MSDeformAttn forward + 12 backward), replayed from the graphs",
                    "weights": "random init", "gt_boxes_per_frame": N_GT,
                    "l2": "no explicit flush: one step streams >1 GB of activations/weights, far above the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": host_frames.numel() * 4,

@@ -33,6 +33,12 @@ CASES = {
     "c1_enc_model": (1, 8, 32, C1, 4, None, "model"),
     "c5_enc_model": (1, 8, 36, C5, 4, None, "model"),
     "c5_dec": (1, 8, 36, C5 * 2, 4, 800, "boxes"),
+    # diagnostics: same number of queries / samples as c2_enc (22223 x 8 heads x 16), one level only
+    "diag_l0_only": (1, 8, 32, [C2[0]], 16, 22223, "uniform"),
+    "diag_l1_only": (1, 8, 32, [C2[1]], 16, 22223, "uniform"),
+    "diag_l2_only": (1, 8, 32, [C2[2]], 16, 22223, "uniform"),
+    "diag_l3_only": (1, 8, 32, [C2[3]], 16, 22223, "uniform"),
+    "diag_l0_local": (1, 8, 32, [C2[0]], 16, 16700, "rowmajor"),
 }
 
 HEAD_DIRS = torch.tensor([[-1, -1], [-1, 0], [-1, 1], [0, -1], [0, 1], [1, -1], [1, 0], [1, 1]], dtype=torch.float32)
@@ -49,6 +55,13 @@ def make_case(name, dev, seed=0):
     value = torch.randn(N, S, M, D, generator=g)
     if dist == "uniform":
         loc = torch.rand(N, Lq, M, L, P, 2, generator=g)
+    elif dist == "rowmajor":   # query q sits at pixel q of the (single) level, samples within +-3 px
+        h, w = hw[0]
+        q = torch.arange(Lq)
+        cx = ((q % w).float() + 0.5) / w
+        cy = ((q // w).float() + 0.5) / h
+        ref = torch.stack([cx, cy], -1)[None, :, None, None, None, :]
+        loc = ref + (torch.rand(N, Lq, M, L, P, 2, generator=g) - 0.5) * torch.tensor([6.0 / w, 6.0 / h])
     else:
         if enc:   # encoder reference points: pixel centres of every level (deformable_transformer.py:306-319)
             refs = []

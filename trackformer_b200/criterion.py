@@ -100,22 +100,29 @@ class SetCriterion(nn.Module):
 
     def forward(self, outputs, targets):
         last = {k: v for k, v in outputs.items() if k != "aux_outputs"}
-        indices = self.matcher(last, targets)
-        num_boxes = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float,
-                                    device=next(iter(outputs.values())).device)
+        aux_list = list(outputs.get("aux_outputs", ()))
+        if hasattr(self.matcher, "match_layers"):
+            all_indices = self.matcher.match_layers([last] + aux_list, targets)     # one host sync for all layers
+        else:
+            all_indices = [self.matcher(o, targets) for o in [last] + aux_list]
+        indices = all_indices[0]
+
+        n_boxes = sum(len(t["labels"]) for t in targets)
         if is_dist_avail_and_initialized():
-            torch.distributed.all_reduce(num_boxes)
-        num_boxes = torch.clamp(num_boxes / get_world_size(), min=1).item()
+            t = torch.as_tensor([n_boxes], dtype=torch.float, device=next(iter(outputs.values())).device)
+            torch.distributed.all_reduce(t)
+            num_boxes = torch.clamp(t / get_world_size(), min=1).item()
+        else:
+            num_boxes = float(max(n_boxes, 1))
 
         losses = {}
         for name in self.losses:
             losses.update(self.get_loss(name, outputs, targets, indices, num_boxes))
-        for i, aux in enumerate(outputs.get("aux_outputs", ())):
-            aux_indices = self.matcher(aux, targets)
+        for i, aux in enumerate(aux_list):
             for name in self.losses:
                 if name == "masks":
                     continue
                 kw = {"log": False} if name == "labels" else {}
-                part = self.get_loss(name, aux, targets, aux_indices, num_boxes, **kw)
+                part = self.get_loss(name, aux, targets, all_indices[i + 1], num_boxes, **kw)
                 losses.update({f"{k}_{i}": v for k, v in part.items()})
         return losses

@@ -25,7 +25,7 @@
 
 #include "../../include/msda_b200.h"
 #include "msda_common.cuh"
-#include "msda_fwd_d32.cuh"
+#include "msda_d32.cuh"
 
 namespace msda {
 
@@ -228,6 +228,14 @@ static bool aligned16(const T* p) { return (reinterpret_cast<uintptr_t>(p) & 15u
   msda_bwd_kernel<T, VEC_, G_, IT_><<<grid_for(G_), kThreads, 0, st>>>(                      \
       value, shapes, loc, attn, gout, gval, gloc, gattn, d.S, d.M, d.D, d.L, d.Lq, d.P, groups)
 
+// Strip length (iterations of 32 groups) per CTA for the d32 kernels: keep at least ~2 waves of CTAs in
+// flight on 148 SMs, but let big problems walk contiguous strips so neighbouring queries share L1 lines.
+static int pick_iters(int64_t ctas) {
+  const int64_t two_waves = 148 * 8 * 2;
+  int it = int(ctas / two_waves);
+  return it < 1 ? 1 : (it > 8 ? 8 : it);
+}
+
 // Picks lanes-per-group G and packs-per-lane ITERS for `npacks` 16-byte packs per head.
 static void pick_shape(int npacks, int* G, int* iters) {
   int g = 1;
@@ -241,26 +249,29 @@ template <typename T>
 static int forward_impl(const T* value, const int64_t* shapes, const T* loc, const T* attn, T* out,
                         const Dims& d, cudaStream_t st) {
   if (int rc = check_dims(d)) return rc;
-  if (!value || !shapes || !loc || !attn || !out) return MSDA_E_NULLPTR;
   const int64_t groups = int64_t(d.N) * d.Lq * d.M;
-  if (groups == 0) return 0;
+  if (groups == 0) return 0;                       // empty batch / no queries: nothing to do (pointers may be NULL)
+  if (!value || !shapes || !loc || !attn || !out) return MSDA_E_NULLPTR;
   constexpr int V16 = 16 / int(sizeof(T));
   const bool vec_ok = (d.D % V16 == 0) && aligned16(value) && aligned16(out);
   auto grid_for = [&](int G) { return unsigned((groups * G + kThreads - 1) / kThreads); };
   bool launched = false;
   if constexpr (sizeof(T) == 4) {
-    // staged kernels for the shipped geometry (fp32, 128-byte head rows)
+    // specialised kernels for the shipped geometry (fp32, 128-byte head rows); variant 1 forces the generic path
     const int variant = g_fwd_variant.load(std::memory_order_relaxed);
     const int LP = d.L * d.P;
-    if (vec_ok && d.D == 32 && LP <= kMaxLP && aligned16(loc) && (variant == MODE_ROWS || variant == MODE_TAPS)) {
-      const unsigned grid = unsigned((groups + kGroupsPerCta - 1) / kGroupsPerCta);
-      const size_t smem = fwd_d32_smem_bytes(variant, LP);
-      if (variant == MODE_ROWS)
-        msda_fwd_d32_kernel<MODE_ROWS><<<grid, kFwdThreads, smem, st>>>(value, shapes, loc, attn, out, d.S, d.M,
-                                                                        d.L, d.Lq, d.P, groups);
+    if (variant != 1 && vec_ok && d.D == 32 && LP <= kMaxLP && aligned16(loc) && aligned16(attn) &&
+        groups < (int64_t(1) << 31)) {
+      const int64_t ctas = (groups + kGroupsPerCta - 1) / kGroupsPerCta;
+      const int iters = variant >= 2 ? variant - 1 : pick_iters(ctas);
+      const unsigned grid = unsigned((ctas + iters - 1) / iters);
+      const size_t smem = fwd_d32_smem_bytes(LP);
+      if (d.M == 8)
+        msda_fwd_d32_kernel<256><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, out, d.S, d.M, d.L, d.Lq,
+                                                                  d.P, uint32_t(groups), iters);
       else
-        msda_fwd_d32_kernel<MODE_TAPS><<<grid, kFwdThreads, smem, st>>>(value, shapes, loc, attn, out, d.S, d.M,
-                                                                        d.L, d.Lq, d.P, groups);
+        msda_fwd_d32_kernel<0><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, out, d.S, d.M, d.L, d.Lq,
+                                                                d.P, uint32_t(groups), iters);
       launched = true;
     }
   }
@@ -292,18 +303,37 @@ template <typename T>
 static int backward_impl(const T* value, const int64_t* shapes, const T* loc, const T* attn,
                          const T* gout, T* gval, T* gloc, T* gattn, const Dims& d, cudaStream_t st) {
   if (int rc = check_dims(d)) return rc;
-  if (!value || !shapes || !loc || !attn || !gout || !gval || !gloc || !gattn) return MSDA_E_NULLPTR;
   if (d.N > 0) {
+    if (!gval) return MSDA_E_NULLPTR;
     cudaError_t e = cudaMemsetAsync(gval, 0, sizeof(T) * size_t(d.N) * d.S * d.M * d.D, st);
     if (e != cudaSuccess) return int(e);
   }
   const int64_t groups = int64_t(d.N) * d.Lq * d.M;
-  if (groups == 0) return 0;
+  if (groups == 0) return 0;                       // no queries: grad_value is all zeros, the rest is empty
+  if (!value || !shapes || !loc || !attn || !gout || !gloc || !gattn) return MSDA_E_NULLPTR;
   constexpr int V16 = 16 / int(sizeof(T));
   const bool vec_ok = (d.D % V16 == 0) && aligned16(value) && aligned16(gout) && aligned16(gval);
   auto grid_for = [&](int G) { return unsigned((groups * G + kThreads - 1) / kThreads); };
   bool launched = false;
-  if (vec_ok) {
+  if constexpr (sizeof(T) == 4) {
+    const int variant = g_bwd_variant.load(std::memory_order_relaxed);
+    const int LP = d.L * d.P;
+    if (variant != 1 && vec_ok && d.D == 32 && LP <= kMaxLP && aligned16(loc) && aligned16(attn) &&
+        aligned16(gloc) && aligned16(gattn) && groups < (int64_t(1) << 31)) {
+      const int64_t ctas = (groups + kGroupsPerCta - 1) / kGroupsPerCta;
+      const int iters = variant >= 2 ? variant - 1 : pick_iters(ctas);
+      const unsigned grid = unsigned((ctas + iters - 1) / iters);
+      const size_t smem = bwd_d32_smem_bytes(LP);
+      if (d.M == 8)
+        msda_bwd_d32_kernel<256><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, gout, gval, gloc, gattn,
+                                                                  d.S, d.M, d.L, d.Lq, d.P, uint32_t(groups), iters);
+      else
+        msda_bwd_d32_kernel<0><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, gout, gval, gloc, gattn,
+                                                                d.S, d.M, d.L, d.Lq, d.P, uint32_t(groups), iters);
+      launched = true;
+    }
+  }
+  if (!launched && vec_ok) {
     int G, it;
     pick_shape(d.D / V16, &G, &it);
     launched = true;

@@ -70,6 +70,7 @@ class DeformableTransformerEncoder(nn.Module):
         super().__init__()
         self.layers = _clones(encoder_layer, num_layers)
         self.num_layers = num_layers
+        self._ref_memo = {}
 
     @staticmethod
     def get_reference_points(spatial_shapes, valid_ratios, device):
@@ -88,7 +89,15 @@ class DeformableTransformerEncoder(nn.Module):
         return ref[:, :, None] * valid_ratios[:, None]
 
     def forward(self, src, spatial_shapes, valid_ratios, pos=None, padding_mask=None):
-        ref = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device)
+        hw = getattr(spatial_shapes, "_hw_list", None)
+        if hw is not None and padding_mask is None:
+            # dense batch (valid ratios are exactly 1): the grid depends on the level sizes only -- memoise it
+            key = (tuple(hw), src.shape[0], src.device)
+            ref = self._ref_memo.get(key)
+            if ref is None:
+                ref = self._ref_memo[key] = self.get_reference_points(spatial_shapes, valid_ratios, src.device)
+        else:
+            ref = self.get_reference_points(spatial_shapes, valid_ratios, device=src.device)
         out = src
         for layer in self.layers:
             out = layer(out, pos, ref, spatial_shapes, padding_mask)
@@ -192,6 +201,7 @@ class DeformableTransformer(nn.Module):
                                               nhead, dec_n_points), num_decoder_layers, return_intermediate_dec)
         self.level_embed = nn.Parameter(torch.Tensor(num_feature_levels, d_model))
         self.reference_points = nn.Linear(d_model, 2)
+        self._shapes_memo = {}
         self._reset_parameters()
 
     def _reset_parameters(self):
@@ -204,6 +214,17 @@ class DeformableTransformer(nn.Module):
         nn.init.xavier_uniform_(self.reference_points.weight, gain=1.0)
         nn.init.zeros_(self.reference_points.bias)
         nn.init.normal_(self.level_embed)
+
+    def _shapes_tensor(self, hw, device):
+        """[L,2] int64 (H,W) on the device, built once per geometry (no per-forward H2D copy, graph-capture safe);
+        the host copy rides along as ``_hw_list`` so that callees never have to sync to learn the level sizes."""
+        key = (tuple(hw), device)
+        t = self._shapes_memo.get(key)
+        if t is None:
+            t = torch.as_tensor(hw, dtype=torch.long, device=device)
+            t._hw_list = list(hw)
+            self._shapes_memo[key] = t
+        return t
 
     @staticmethod
     def get_valid_ratio(mask):
@@ -226,8 +247,7 @@ class DeformableTransformer(nn.Module):
         src_flat = torch.cat(src_l, 1)
         mask_flat = torch.cat(mask_l, 1)
         pos_flat = torch.cat(pos_l, 1)
-        spatial_shapes = torch.as_tensor(hw, dtype=torch.long, device=src_flat.device)
-        spatial_shapes._hw_list = hw                     # host copy: lets callees skip device syncs
+        spatial_shapes = self._shapes_tensor(hw, src_flat.device)
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
         dense = all(getattr(m, "_no_padding", False) for m in masks)
         enc_mask = None if dense else mask_flat          # an all-False mask is a no-op in MSDeformAttn
@@ -236,8 +256,7 @@ class DeformableTransformer(nn.Module):
             half_s, half_l = src_flat.shape[1] // 2, self.num_feature_levels // 2
 
             def _enc(sl_s, sl_l):
-                shp = spatial_shapes[sl_l]
-                shp._hw_list = hw[sl_l]
+                shp = self._shapes_tensor(hw[sl_l], src_flat.device)
                 return self.encoder(src_flat[:, sl_s], shp, valid_ratios[:, sl_l], pos_flat[:, sl_s],
                                     None if enc_mask is None else enc_mask[:, sl_s])
             prev_memory = _enc(slice(None, half_s), slice(None, half_l))

@@ -28,14 +28,8 @@ class HungarianMatcher(nn.Module):
         self.focal_alpha = focal_alpha
         self.focal_gamma = focal_gamma
 
-    @torch.no_grad()
-    def forward(self, outputs, targets):
-        bs, nq = outputs["pred_logits"].shape[:2]
-        logits = outputs["pred_logits"].flatten(0, 1)
-        boxes = outputs["pred_boxes"].flatten(0, 1)
-        tgt_ids = torch.cat([t["labels"] for t in targets])
-        tgt_boxes = torch.cat([t["boxes"] for t in targets])
-
+    def _cost(self, logits, boxes, tgt_ids, tgt_boxes):
+        """[Q', C] logits, [Q', 4] boxes against all T ground-truth boxes of the batch -> [Q', T] cost."""
         if self.focal_loss:
             p = logits.sigmoid()
             neg = (1 - self.focal_alpha) * (p ** self.focal_gamma) * (-(1 - p + 1e-8).log())
@@ -45,8 +39,38 @@ class HungarianMatcher(nn.Module):
             c_class = -logits.softmax(-1)[:, tgt_ids]
         c_bbox = torch.cdist(boxes, tgt_boxes, p=1)
         c_giou = -generalized_box_iou(box_cxcywh_to_xyxy(boxes), box_cxcywh_to_xyxy(tgt_boxes))
-        cost = self.cost_bbox * c_bbox + self.cost_class * c_class + self.cost_giou * c_giou
-        cost = cost.view(bs, nq, -1).cpu()
+        return self.cost_bbox * c_bbox + self.cost_class * c_class + self.cost_giou * c_giou
+
+    @torch.no_grad()
+    def match_layers(self, outputs_list, targets):
+        """Matchings for several decoder layers with ONE device->host transfer (the reference pays one
+        ``.cpu()`` sync per layer, detr.py:393,412).  Cost values, and therefore the assignments, are the ones
+        ``forward`` computes layer by layer.  Track-query forcing needs per-layer bookkeeping: fall back."""
+        if any("track_query_match_ids" in t for t in targets):
+            return [self.forward(o, targets) for o in outputs_list]
+        bs, nq = outputs_list[0]["pred_logits"].shape[:2]
+        tgt_ids = torch.cat([t["labels"] for t in targets])
+        tgt_boxes = torch.cat([t["boxes"] for t in targets])
+        sizes = [len(t["boxes"]) for t in targets]
+        k = len(outputs_list)
+        logits = torch.stack([o["pred_logits"] for o in outputs_list]).flatten(0, 2)
+        boxes = torch.stack([o["pred_boxes"] for o in outputs_list]).flatten(0, 2)
+        cost = self._cost(logits, boxes, tgt_ids, tgt_boxes).view(k, bs, nq, -1).cpu()
+        result = []
+        for layer in cost:
+            picks = [linear_sum_assignment(c[i]) for i, c in enumerate(layer.split(sizes, -1))]
+            result.append([(torch.as_tensor(r, dtype=torch.int64), torch.as_tensor(c, dtype=torch.int64))
+                           for r, c in picks])
+        return result
+
+    @torch.no_grad()
+    def forward(self, outputs, targets):
+        bs, nq = outputs["pred_logits"].shape[:2]
+        logits = outputs["pred_logits"].flatten(0, 1)
+        boxes = outputs["pred_boxes"].flatten(0, 1)
+        tgt_ids = torch.cat([t["labels"] for t in targets])
+        tgt_boxes = torch.cat([t["boxes"] for t in targets])
+        cost = self._cost(logits, boxes, tgt_ids, tgt_boxes).view(bs, nq, -1).cpu()
 
         sizes = [len(t["boxes"]) for t in targets]
         for i, t in enumerate(targets):

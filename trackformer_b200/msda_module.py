@@ -14,8 +14,6 @@ Host-side differences (results identical up to fp32 rounding):
 """
 from __future__ import annotations
 
-import math
-
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -68,7 +66,11 @@ class MSDeformAttn(nn.Module):
         n, len_q, _ = query.shape
         _, len_in, _ = input_flatten.shape
         m, lv, pt = self.n_heads, self.n_levels, self.n_points
-        assert int((input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum()) == len_in
+        hw = getattr(input_spatial_shapes, "_hw_list", None)      # host copy attached by the transformer
+        if hw is not None:
+            assert sum(h * w for h, w in hw) == len_in
+        else:                                                       # reference behaviour: device reduction + sync
+            assert int((input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum()) == len_in
 
         value = self.value_proj(input_flatten)
         if input_padding_mask is not None:

@@ -39,7 +39,9 @@ def nested_tensor_from_tensor_list(images: Sequence[Tensor]) -> NestedTensor:
         if images.ndim != 4:
             raise ValueError("not supported")
         b, _, h, w = images.shape
-        return NestedTensor(images, torch.zeros((b, h, w), dtype=torch.bool, device=images.device))
+        mask = torch.zeros((b, h, w), dtype=torch.bool, device=images.device)
+        mask._no_padding = True                           # known without looking at the data (no host sync)
+        return NestedTensor(images, mask)
     first = images[0]
     if first.ndim != 3:
         raise ValueError("not supported")
@@ -84,10 +86,20 @@ def box_iou(a: Tensor, b: Tensor):
     return inter / union, union
 
 
+def _check_boxes(b: Tensor) -> None:
+    """Degenerate boxes give inf/nan GIoU: the reference asserts (box_ops.py:51-52).  On CUDA the check is
+    asynchronous (device-side assert) so it does not stall the host once per call."""
+    ok = (b[:, 2:] >= b[:, :2]).all()
+    if b.is_cuda:
+        torch._assert_async(ok)
+    else:
+        assert ok
+
+
 def generalized_box_iou(a: Tensor, b: Tensor) -> Tensor:
     """Pairwise GIoU of xyxy boxes -> [len(a), len(b)]."""
-    assert (a[:, 2:] >= a[:, :2]).all()
-    assert (b[:, 2:] >= b[:, :2]).all()
+    _check_boxes(a)
+    _check_boxes(b)
     iou, union = box_iou(a, b)
     lt = torch.min(a[:, None, :2], b[:, :2])
     rb = torch.max(a[:, None, 2:], b[:, 2:])
