@@ -306,19 +306,36 @@ def test_full_size_properties(msda, dev, cfg):
     gv1, _, _ = msda.ms_deform_attn_backward(value, shapes, loc_in, attn, torch.ones_like(out), 64)
     torch.testing.assert_close(gv1.double().sum(), torch.tensor(float(D * N * Lq * M), dtype=torch.float64, device=dev),
                                rtol=1e-4, atol=1.0)
-    # (5) finite-difference check of grad_loc on a few coordinates (fp32: loose)
-    idx = torch.randint(0, loc.numel(), (8,), generator=torch.Generator().manual_seed(1)).tolist()
-    eps = 1e-3
+    # (5) finite-difference check of grad_loc on a few coordinates.  One location element only moves one
+    #     (q, m) output row; bilinear interpolation is piecewise linear, so the central difference is exact
+    #     unless the +-eps probe crosses a pixel border (skipped) -- what remains is fp32 rounding.
+    L = len(hw)
+    eps = 2e-5
+    checked = 0
+    gen = torch.Generator().manual_seed(1)
     flat_gl = gl.reshape(-1)
-    for i in idx:
+    for i in torch.randint(0, loc.numel(), (24,), generator=gen).tolist():
+        c = i % 2
+        p_ = (i // 2) % P
+        l_ = (i // (2 * P)) % L
+        m_ = (i // (2 * P * L)) % M
+        q_ = (i // (2 * P * L * M)) % Lq
+        size = hw[l_][1] if c == 0 else hw[l_][0]
+        t = float(loc.reshape(-1)[i]) * size - 0.5
+        import math
+        if not (0.0 < t < size - 1.0) or math.floor(t - 2 * eps * size) != math.floor(t + 2 * eps * size):
+            continue
         lp, lm = loc.clone().reshape(-1), loc.clone().reshape(-1)
         lp[i] += eps
         lm[i] -= eps
-        op = msda.ms_deform_attn_forward(value, shapes, lp.view_as(loc), attn, 64)
-        om = msda.ms_deform_attn_forward(value, shapes, lm.view_as(loc), attn, 64)
-        fd = ((op.double() - om.double()) * gout.double()).sum() / (2 * eps)
-        # bilinear is piecewise linear: the central difference is exact unless a cell border is crossed
-        assert abs(fd.item() - flat_gl[i].item()) <= 0.05 * (abs(fd.item()) + abs(flat_gl[i].item())) + 0.5, (i, fd.item(), flat_gl[i].item())
+        op = msda.ms_deform_attn_forward(value, shapes, lp.view_as(loc), attn, 64)[0, q_, m_ * D:(m_ + 1) * D]
+        om = msda.ms_deform_attn_forward(value, shapes, lm.view_as(loc), attn, 64)[0, q_, m_ * D:(m_ + 1) * D]
+        g_row = gout[0, q_, m_ * D:(m_ + 1) * D].double()
+        fd = float(((op.double() - om.double()) * g_row).sum() / (float(lp[i]) - float(lm[i])))
+        got = float(flat_gl[i])
+        assert abs(fd - got) <= 0.03 * (abs(fd) + abs(got)) + 0.5, (i, fd, got)
+        checked += 1
+    assert checked >= 8
 
 
 def test_backward_determinism_of_loc_and_attn_grads(msda, dev):

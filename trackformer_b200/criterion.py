@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .util import (accuracy, box_cxcywh_to_xyxy, generalized_box_iou, get_world_size,
-                   is_dist_avail_and_initialized, sigmoid_focal_loss)
+                   is_dist_avail_and_initialized, paired_giou, sigmoid_focal_loss)
 
 
 class SetCriterion(nn.Module):
@@ -125,4 +125,79 @@ class SetCriterion(nn.Module):
                 kw = {"log": False} if name == "labels" else {}
                 part = self.get_loss(name, aux, targets, all_indices[i + 1], num_boxes, **kw)
                 losses.update({f"{k}_{i}": v for k, v in part.items()})
+        return losses
+
+    # ------------------------------------------------------------------------------------------
+    def _num_boxes(self, targets, device):
+        n_boxes = sum(len(t["labels"]) for t in targets)
+        if is_dist_avail_and_initialized():
+            t = torch.as_tensor([n_boxes], dtype=torch.float, device=device)
+            torch.distributed.all_reduce(t)
+            return torch.clamp(t / get_world_size(), min=1).item()
+        return float(max(n_boxes, 1))
+
+    def forward_stacked(self, logits, boxes, targets):
+        """Same losses as ``forward`` for a detector whose K decoder layers arrive stacked --
+        ``logits [K,B,Q,C]``, ``boxes [K,B,Q,4]``, last layer = final prediction -- computed in ONE pass over
+        all layers instead of K passes (the reference loops, detr.py:404-424): one Hungarian transfer, one focal
+        loss, one L1/GIoU evaluation.  Keys and values equal ``forward`` on the equivalent dict (up to fp32
+        summation order); falls back to it for the cases that need per-layer bookkeeping."""
+        k, bs, nq, _ = logits.shape
+        layers = [{"pred_logits": logits[i], "pred_boxes": boxes[i]} for i in range(k)]
+        special = (not self.focal_loss or set(self.losses) != {"labels", "boxes", "cardinality"}
+                   or any("track_query_match_ids" in t for t in targets) or not hasattr(self.matcher, "match_layers"))
+        sizes = [len(t["labels"]) for t in targets]
+        if special or min(sizes) == 0 or max(sizes) > nq:
+            out = dict(layers[-1])
+            out["aux_outputs"] = layers[:-1]
+            return self.forward(out, targets)
+
+        all_indices = self.matcher.match_layers(layers, targets)            # [K][B] (src, tgt) on the host
+        num_boxes = self._num_boxes(targets, logits.device)
+        dev = logits.device
+        per_layer = sum(sizes)
+        lay = torch.arange(k).repeat_interleave(per_layer)
+        bat = torch.cat([torch.full_like(src, b) for ind in all_indices for b, (src, _) in enumerate(ind)])
+        src = torch.cat([s_ for ind in all_indices for (s_, _) in ind])
+        tgt = torch.cat([t_ + off for ind in all_indices
+                         for (_, t_), off in zip(ind, [sum(sizes[:b]) for b in range(bs)])])
+        idx = torch.stack([lay, bat, src, tgt]).to(dev, non_blocking=True)
+        lay, bat, src, tgt = idx[0], idx[1], idx[2], idx[3]
+        gt_labels = torch.cat([t["labels"] for t in targets])[tgt]
+        gt_boxes = torch.cat([t["boxes"] for t in targets])[tgt]
+
+        # labels: sigmoid focal loss against one-hot targets (no-object = all zeros)
+        classes = torch.full((k, bs, nq), self.num_classes, dtype=torch.int64, device=dev)
+        classes[lay, bat, src] = gt_labels
+        onehot = torch.zeros((k, bs, nq, logits.shape[-1] + 1), dtype=logits.dtype, device=dev)
+        onehot.scatter_(3, classes.unsqueeze(-1), 1)
+        onehot = onehot[..., :-1]
+        p = logits.sigmoid()
+        ce = F.binary_cross_entropy_with_logits(logits, onehot, reduction="none")
+        p_t = p * onehot + (1 - p) * (1 - onehot)
+        focal = ce * ((1 - p_t) ** self.focal_gamma)
+        if self.focal_alpha >= 0:
+            focal = (self.focal_alpha * onehot + (1 - self.focal_alpha) * (1 - onehot)) * focal
+        loss_ce = focal.mean(2).sum((1, 2)) / num_boxes * nq                                   # [K]
+
+        # boxes: L1 + GIoU over the matched pairs of every layer
+        matched = boxes[lay, bat, src]
+        loss_bbox = (matched - gt_boxes).abs().view(k, per_layer, 4).sum((1, 2)) / num_boxes
+        giou = paired_giou(box_cxcywh_to_xyxy(matched), box_cxcywh_to_xyxy(gt_boxes))
+        loss_giou = (1 - giou).view(k, per_layer).sum(1) / num_boxes
+
+        with torch.no_grad():
+            n_gt = torch.as_tensor(sizes, device=dev, dtype=torch.float)
+            n_pred = (logits.argmax(-1) != logits.shape[-1] - 1).sum(2).float()                  # [K,B]
+            card = (n_pred - n_gt[None]).abs().mean(1)                                           # [K]
+            last = slice((k - 1) * per_layer, None)
+            class_error = 100 - accuracy(logits[-1][bat[last], src[last]], gt_labels[last])[0]
+
+        losses = {"loss_ce": loss_ce[-1], "class_error": class_error, "loss_bbox": loss_bbox[-1],
+                  "loss_giou": loss_giou[-1], "cardinality_error": card[-1]}
+        for i in range(k - 1):
+            losses[f"loss_ce_{i}"] = loss_ce[i]
+            losses[f"loss_bbox_{i}"] = loss_bbox[i]
+            losses[f"loss_giou_{i}"] = loss_giou[i]
+            losses[f"cardinality_error_{i}"] = card[i]
         return losses

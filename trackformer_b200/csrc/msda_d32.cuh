@@ -77,6 +77,17 @@ __device__ __forceinline__ void axis_window(float t, int size, int& b, float& wa
   }
 }
 
+// Which of the CTA's 32 consecutive (q, m) groups the 8-lane group `gl` (= tid/8) works on.
+// With M = 8 heads (STRIDE_CT = 256) a CTA covers 4 queries x 8 heads; mapping warp w -> head w and the
+// warp's four 8-lane groups -> the four queries makes the 4 rows touched by one warp-level LDG/RED belong to
+// NEIGHBOURING QUERIES OF ONE HEAD.  On the coarser levels neighbouring queries sample the same pixels, so
+// the LSU sees 1-2 distinct 128-byte lines per request instead of 4 (an L1 request costs ~2 cycles per
+// distinct line, profiles/).  Other head counts keep memory order.
+template <int STRIDE_CT>
+__device__ __forceinline__ int group_slot(int gl) {
+  return STRIDE_CT == 256 ? ((gl & 3) * 8 + (gl >> 2)) : gl;
+}
+
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
 __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
@@ -106,7 +117,8 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
   int* s_o = reinterpret_cast<int*>(s_w + kGroupsPerCta * pitch);        // [32][pitch] element offset of corner 1
   const int stride = STRIDE_CT ? STRIDE_CT : M * D;
   const int tid = threadIdx.x;
-  const int gl = tid >> 3;      // group inside the CTA
+  const int gl = tid >> 3;      // tap-table row of this thread's group (4 consecutive rows per warp)
+  const int gm = group_slot<STRIDE_CT>(gl);   // which of the CTA's 32 consecutive groups that is
   const int j = tid & 7;        // 16-byte pack inside the head row / tap column inside the prologue
 
   load_level_table(lv, lvl_of, shapes, L, P);
@@ -115,8 +127,8 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
   for (int it = 0; it < iters; ++it) {
     const uint32_t g0 = (uint32_t(blockIdx.x) * iters + it) * kGroupsPerCta;
     if (g0 >= groups) break;                                    // uniform
-    const bool active = g0 + gl < groups;
-    const uint32_t gid = active ? g0 + gl : groups - 1;
+    const bool active = g0 + gm < groups;
+    const uint32_t gid = active ? g0 + gm : groups - 1;
 
     // ---- prologue: every lane builds taps j, j+8, ... of its own group (rows are read coalesced)
     {
@@ -227,6 +239,7 @@ msda_bwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
   const int stride = STRIDE_CT ? STRIDE_CT : M * D;
   const int tid = threadIdx.x;
   const int gl = tid >> 3;
+  const int gm = group_slot<STRIDE_CT>(gl);
   const int j = tid & 7;
 
   load_level_table(lv, lvl_of, shapes, L, P);
@@ -235,8 +248,8 @@ msda_bwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
   for (int it = 0; it < iters; ++it) {
     const uint32_t g0 = (uint32_t(blockIdx.x) * iters + it) * kGroupsPerCta;
     if (g0 >= groups) break;
-    const bool active = g0 + gl < groups;
-    const uint32_t gid = active ? g0 + gl : groups - 1;
+    const bool active = g0 + gm < groups;
+    const uint32_t gid = active ? g0 + gm : groups - 1;
     const size_t sbase = size_t(gid) * LP;
 
     {

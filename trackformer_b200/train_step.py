@@ -10,9 +10,9 @@ plus the gradient all-reduce the reference gets from DistributedDataParallel (sr
 
 Why graphs: an eager PyTorch step of this model issues ~5000 small kernels and is host-bound (58 ms/step
 measured on a B200 box although the kernels themselves need < 20 ms).  The model forward and its
-backward are static-shape, sync-free programs, so they are captured once with
-``torch.cuda.make_graphed_callables`` and replayed -- two graph launches instead of thousands of kernel
-launches.  Between the two sits what cannot be captured: the Hungarian matching (scipy on the host, like the
+backward are static-shape, sync-free programs, so they are captured once (``torch.cuda.CUDAGraph``) and
+replayed -- two graph launches instead of thousands of kernel launches.  The backward graph also contains the
+accumulation into the gradient buffer, so nothing per-parameter runs eagerly.  Between the two sits what cannot be captured: the Hungarian matching (scipy on the host, like the
 reference, matcher.py:104,127 -- the index bookkeeping must stay bit-exact) and the loss, which is small.
 
 Multi-GPU: one process per GPU.  Gradients live in ONE flat fp32 buffer (every ``param.grad`` is a view into
@@ -54,7 +54,7 @@ class TrainStep:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.params: List[nn.Parameter] = [p for p in model.parameters() if p.requires_grad]
         self.core = _DetectorCore(model)
-        self.graphed = None
+        self.g_fwd = self.g_bwd = None
 
         # flat gradient buffer: param.grad are views -> one zero-fill, one all-reduce, one norm
         total = sum(p.numel() for p in self.params)
@@ -65,28 +65,58 @@ class TrainStep:
             p.grad = self.flat_grad[ofs:ofs + p.numel()].view_as(p)
             ofs += p.numel()
         self.optimizer = optimizer_factory(self.params) if optimizer_factory is not None else None
-
         if use_graphs:
             assert example_frames is not None and example_frames.is_cuda
-            # make_graphed_callables warms up on a side stream (cuDNN autotuning, position-encoding / grid memos)
-            # and captures the forward and the backward as two graphs bound to one autograd node
-            self.graphed = torch.cuda.make_graphed_callables(self.core, (example_frames,), num_warmup_iters=3)
-            self.flat_grad.zero_()
+            self._capture(example_frames)
 
     # ------------------------------------------------------------------------------------------
-    def _outputs(self, logits, boxes) -> Dict:
-        out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1]}
-        out["aux_outputs"] = [{"pred_logits": a, "pred_boxes": b} for a, b in zip(logits[:-1], boxes[:-1])]
-        return out
+    def _capture(self, example: torch.Tensor) -> None:
+        """Two graphs sharing one memory pool: (1) the model forward, (2) zero-fill of the flat gradient +
+        the whole model backward INCLUDING the accumulation into the flat gradient views -- so a replay leaves the
+        finished gradient in ``flat_grad`` with no per-parameter eager work."""
+        self.static_frames = example.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up off the capture path: cuDNN autotuning, memos
+            for _ in range(3):
+                lg, bx = self.core(self.static_frames)
+                torch.autograd.backward((lg, bx), (torch.zeros_like(lg), torch.zeros_like(bx)))
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        pool = torch.cuda.graph_pool_handle()
+        self.g_fwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_fwd, pool=pool):
+            self.s_logits, self.s_boxes = self.core(self.static_frames)
+        self.s_glogits = torch.zeros_like(self.s_logits)
+        self.s_gboxes = torch.zeros_like(self.s_boxes)
+        self.g_bwd = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g_bwd, pool=pool):
+            self.flat_grad.zero_()
+            torch.autograd.backward((self.s_logits, self.s_boxes), (self.s_glogits, self.s_gboxes))
+        self.flat_grad.zero_()
+
+    def _loss(self, logits, boxes, targets):
+        loss_dict = self.criterion.forward_stacked(logits, boxes, targets)
+        wd = self.criterion.weight_dict
+        return sum(loss_dict[k] * wd[k] for k in loss_dict if k in wd)
 
     def __call__(self, frames: torch.Tensor, targets: list) -> torch.Tensor:
-        fn = self.graphed if self.graphed is not None else self.core
-        logits, boxes = fn(frames)
-        loss_dict = self.criterion(self._outputs(logits, boxes), targets)
-        wd = self.criterion.weight_dict
-        loss = sum(loss_dict[k] * wd[k] for k in loss_dict if k in wd)
-        self.flat_grad.zero_()
-        loss.backward()
+        if self.g_fwd is not None:
+            if frames is not self.static_frames:
+                self.static_frames.copy_(frames, non_blocking=True)     # device or pinned-host source
+            self.g_fwd.replay()
+            logits = self.s_logits.detach().requires_grad_(True)
+            boxes = self.s_boxes.detach().requires_grad_(True)
+            loss = self._loss(logits, boxes, targets)
+            g_logits, g_boxes = torch.autograd.grad(loss, (logits, boxes))
+            self.s_glogits.copy_(g_logits)
+            self.s_gboxes.copy_(g_boxes)
+            self.g_bwd.replay()
+        else:
+            logits, boxes = self.core(frames)
+            loss = self._loss(logits, boxes, targets)
+            self.flat_grad.zero_()
+            loss.backward()
         if self.world > 1:
             dist.all_reduce(self.flat_grad)
             self.flat_grad.div_(self.world)

@@ -108,6 +108,19 @@ def generalized_box_iou(a: Tensor, b: Tensor) -> Tensor:
     return iou - (hull - union) / hull
 
 
+def paired_giou(a: Tensor, b: Tensor) -> Tensor:
+    """GIoU of box pairs (a[i], b[i]) -- the diagonal of ``generalized_box_iou(a, b)`` without the matrix."""
+    _check_boxes(a)
+    _check_boxes(b)
+    area_a, area_b = _area(a), _area(b)
+    wh = (torch.min(a[:, 2:], b[:, 2:]) - torch.max(a[:, :2], b[:, :2])).clamp(min=0)
+    inter = wh[:, 0] * wh[:, 1]
+    union = area_a + area_b - inter
+    hull_wh = (torch.max(a[:, 2:], b[:, 2:]) - torch.min(a[:, :2], b[:, :2])).clamp(min=0)
+    hull = hull_wh[:, 0] * hull_wh[:, 1]
+    return inter / union - (hull - union) / hull
+
+
 # ----------------------------------------------------------------------------- losses
 def sigmoid_focal_loss(logits: Tensor, targets: Tensor, num_boxes: float, alpha: float = 0.25,
                        gamma: float = 2) -> Tensor:
