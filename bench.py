@@ -127,6 +127,9 @@ def cpu_reference_arm(steps, warmup, batch):
 
     saved = mm.MSDeformAttnFunction
     mm.MSDeformAttnFunction = _CpuFn
+    # all the host threads the CPU path can use (torchrun pins OMP_NUM_THREADS=1 by default): one per physical core
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(max(torch.get_num_threads(), ncpu // 2 if ncpu > 16 else ncpu))
     try:
         torch.manual_seed(0)
         model, criterion, _ = build_model(default_args(device="cpu"))

@@ -1,0 +1,45 @@
+/*
+ * tfb200_fused.h -- C ABI of the fused transformer-layer kernels in libmsda_b200.so (sm_100a).
+ *
+ * These have NO counterpart in the reference's native code: the reference runs them as chains of PyTorch ops
+ *   x = norm(x + dropout(branch))        src/trackformer/models/deformable_transformer.py:284-285, 291-292,
+ *                                        360-361, 370-371, 377-378
+ * They sit on the hot path and are exposed through the same Python module as extra
+ * functions; the reference-facing surface stays include/msda_b200.h.
+ *
+ * Conventions as in msda_b200.h: caller owns all (device) buffers, work is enqueued on `stream`, 0 = success,
+ * negative = argument error, positive = cudaError_t.
+ */
+#ifndef TFB200_FUSED_H_
+#define TFB200_FUSED_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFB200_E_NULLPTR (-1)
+#define TFB200_E_SHAPE   (-2)   /* C must be a multiple of 128, <= 512 (backward) / 1024 (forward) */
+#define TFB200_LN_MAX_CTAS 592  /* persistent grid: 148 SMs x 4 CTAs; also the row count of `partial_ws` */
+
+/* number of CTAs (= rows of the [ctas][2][C] fp32 workspace the backward needs) for a problem of `rows` rows */
+int tfb200_ln_partial_ctas(int64_t rows);
+
+/* s = x + branch * keep_mask / keep_prob   (keep_mask == NULL: s = x + branch)
+ * y = LayerNorm(s) * gamma + beta          mean/rstd [rows] and s_out [rows][C] are optional outputs (NULL to skip) */
+int tfb200_add_dropout_layernorm_fwd_f32(const float* x, const float* branch, const uint8_t* keep_mask,
+                                         const float* gamma, const float* beta, float* s_out, float* y,
+                                         float* mean, float* rstd, int64_t rows, int C, float keep_prob, float eps,
+                                         void* stream);
+
+/* dx = dL/dx (= dL/ds), dbranch = dL/dbranch (NULL to skip), dgamma/dbeta [C]; partial_ws: [ctas][2][C] fp32 */
+int tfb200_add_dropout_layernorm_bwd_f32(const float* dy, const float* s, const uint8_t* keep_mask,
+                                         const float* gamma, const float* mean, const float* rstd, float* dx,
+                                         float* dbranch, float* dgamma, float* dbeta, float* partial_ws,
+                                         int64_t rows, int C, float keep_prob, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFB200_FUSED_H_ */

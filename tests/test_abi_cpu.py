@@ -20,9 +20,13 @@ def lib():
 
 
 def declared_functions():
-    src = open(HEADER).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(msda_b200_\w+)\s*\(", src)))
+    names = set()
+    inc = os.path.dirname(HEADER)
+    for h in sorted(os.listdir(inc)):
+        if h.endswith(".h"):
+            src = re.sub(r"/\*.*?\*/", "", open(os.path.join(inc, h)).read(), flags=re.S)
+            names |= set(re.findall(r"\b((?:msda_b200|tfb200)_\w+)\s*\(", src))
+    return sorted(names)
 
 
 def test_header_declares_expected_entry_points():

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/msda_b200.h"
+#include "../../include/tfb200_fused.h"
 
 namespace {
 
@@ -130,6 +131,64 @@ std::vector<at::Tensor> ms_deform_attn_backward(const at::Tensor& value, const a
   return {grad_value, grad_loc, grad_attn};
 }
 
+// ---- fused residual + dropout + LayerNorm (include/tfb200_fused.h) -------------------------------------------
+// forward: returns {y, s, mean, rstd}; keep_mask is an optional bool/uint8 tensor of x's shape
+std::vector<at::Tensor> add_dropout_layernorm_forward(const at::Tensor& x, const at::Tensor& branch,
+                                                      const c10::optional<at::Tensor>& keep_mask,
+                                                      const at::Tensor& gamma, const at::Tensor& beta,
+                                                      double keep_prob, double eps) {
+  TORCH_CHECK(x.is_cuda() && branch.is_cuda(), "add_dropout_layernorm: CUDA tensors required (no CPU path)");
+  TORCH_CHECK(x.scalar_type() == at::kFloat && branch.scalar_type() == at::kFloat, "fp32 only");
+  TORCH_CHECK(x.sizes() == branch.sizes(), "x and branch must have the same shape");
+  const int64_t C = x.size(-1);
+  const at::Tensor xc = x.contiguous(), bc = branch.contiguous(), g = gamma.contiguous(), b = beta.contiguous();
+  const int64_t rows = xc.numel() / C;
+  const c10::cuda::CUDAGuard guard(x.device());
+  at::Tensor y = at::empty_like(xc), s = at::empty_like(xc);
+  at::Tensor mean = at::empty({rows}, xc.options()), rstd = at::empty({rows}, xc.options());
+  const uint8_t* mptr = nullptr;
+  at::Tensor mk;
+  if (keep_mask.has_value() && keep_mask->defined()) {
+    mk = keep_mask->contiguous();
+    TORCH_CHECK(mk.numel() == xc.numel() && mk.element_size() == 1, "keep_mask must be a bool/uint8 tensor shaped like x");
+    mptr = static_cast<const uint8_t*>(mk.data_ptr());
+  }
+  const int rc = tfb200_add_dropout_layernorm_fwd_f32(
+      xc.data_ptr<float>(), bc.data_ptr<float>(), mptr, g.data_ptr<float>(), b.data_ptr<float>(), s.data_ptr<float>(),
+      y.data_ptr<float>(), mean.data_ptr<float>(), rstd.data_ptr<float>(), rows, int(C), float(keep_prob), float(eps),
+      c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "add_dropout_layernorm_forward failed (code ", rc, "): C must be a multiple of 128 and <= 512");
+  return {y, s, mean, rstd};
+}
+
+// backward: returns {dx, dbranch, dgamma, dbeta}
+std::vector<at::Tensor> add_dropout_layernorm_backward(const at::Tensor& dy, const at::Tensor& s,
+                                                       const c10::optional<at::Tensor>& keep_mask,
+                                                       const at::Tensor& gamma, const at::Tensor& mean,
+                                                       const at::Tensor& rstd, double keep_prob) {
+  TORCH_CHECK(dy.is_cuda() && s.is_cuda(), "add_dropout_layernorm: CUDA tensors required (no CPU path)");
+  const int64_t C = s.size(-1);
+  const at::Tensor dyc = dy.contiguous(), g = gamma.contiguous();
+  const int64_t rows = s.numel() / C;
+  const c10::cuda::CUDAGuard guard(s.device());
+  at::Tensor dx = at::empty_like(s), db = at::empty_like(s);
+  at::Tensor dgamma = at::empty({C}, s.options()), dbeta = at::empty({C}, s.options());
+  at::Tensor ws = at::empty({tfb200_ln_partial_ctas(rows), 2, C}, s.options());
+  const uint8_t* mptr = nullptr;
+  at::Tensor mk;
+  if (keep_mask.has_value() && keep_mask->defined()) {
+    mk = keep_mask->contiguous();
+    mptr = static_cast<const uint8_t*>(mk.data_ptr());
+  }
+  const int rc = tfb200_add_dropout_layernorm_bwd_f32(
+      dyc.data_ptr<float>(), s.data_ptr<float>(), mptr, g.data_ptr<float>(), mean.data_ptr<float>(),
+      rstd.data_ptr<float>(), dx.data_ptr<float>(), db.data_ptr<float>(), dgamma.data_ptr<float>(),
+      dbeta.data_ptr<float>(), ws.data_ptr<float>(), rows, int(C), float(keep_prob),
+      c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "add_dropout_layernorm_backward failed (code ", rc, ")");
+  return {dx, db, dgamma, dbeta};
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200 (sm_100a) multi-scale deformable attention; drop-in for the reference extension";
   m.def("ms_deform_attn_forward", &ms_deform_attn_forward, "ms_deform_attn_forward");
@@ -138,4 +197,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("abi_version", []() { return msda_b200_abi_version(); });
   m.def("launch_count", []() { return msda_b200_launch_count(); });
   m.def("set_variant", [](int f, int b) { msda_b200_set_variant(f, b); });
+  m.def("add_dropout_layernorm_forward", &add_dropout_layernorm_forward);
+  m.def("add_dropout_layernorm_backward", &add_dropout_layernorm_backward);
 }

@@ -20,6 +20,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .fused_norm import add_dropout_layernorm
 from .msda_module import MSDeformAttn
 from .util import inverse_sigmoid
 
@@ -57,11 +58,11 @@ class DeformableTransformerEncoderLayer(nn.Module):
 
     def forward_ffn(self, src):
         ff = self.linear2(self.dropout2(self.activation(self.linear1(src))))
-        return self.norm2(src + self.dropout3(ff))
+        return add_dropout_layernorm(src, ff, self.dropout3, self.norm2)
 
     def forward(self, src, pos, reference_points, spatial_shapes, padding_mask=None):
         attn = self.self_attn(_add_pos(src, pos), reference_points, src, spatial_shapes, padding_mask)
-        src = self.norm1(src + self.dropout1(attn))
+        src = add_dropout_layernorm(src, attn, self.dropout1, self.norm1)
         return self.forward_ffn(src)
 
 
@@ -125,18 +126,18 @@ class DeformableTransformerDecoderLayer(nn.Module):
 
     def forward_ffn(self, tgt):
         ff = self.linear2(self.dropout3(self.activation(self.linear1(tgt))))
-        return self.norm3(tgt + self.dropout4(ff))
+        return add_dropout_layernorm(tgt, ff, self.dropout4, self.norm3)
 
     def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, src_padding_mask=None,
                 query_attn_mask=None):
         # query self-attention (dense, tiny: Lq <= ~800) -- sequence-first nn.MultiheadAttention like the reference
         qk = _add_pos(tgt, query_pos).transpose(0, 1)
         sa = self.self_attn(qk, qk, tgt.transpose(0, 1), key_padding_mask=query_attn_mask)[0].transpose(0, 1)
-        tgt = self.norm2(tgt + self.dropout2(sa))
+        tgt = add_dropout_layernorm(tgt, sa, self.dropout2, self.norm2)
         # deformable cross-attention into the encoder memory
         ca = self.cross_attn(_add_pos(tgt, query_pos), reference_points, src, src_spatial_shapes,
                              src_padding_mask, query_attn_mask)
-        tgt = self.norm1(tgt + self.dropout1(ca))
+        tgt = add_dropout_layernorm(tgt, ca, self.dropout1, self.norm1)
         return self.forward_ffn(tgt)
 
 

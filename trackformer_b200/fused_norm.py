@@ -1,0 +1,52 @@
+"""``x = LayerNorm(x + dropout(branch))`` as one fused sm_100a kernel per direction.
+
+Replaces the three-op forward / four-op backward chain the reference's transformer layers execute for every
+residual connection (src/trackformer/models/deformable_transformer.py:284-285, 291-292, 360-361, 370-371,
+377-378).  Same arithmetic (biased variance, eps inside the rsqrt, inverted dropout scaling 1/(1-p)); the
+dropout mask is drawn with torch's generator (graph-capture safe) and consumed by the kernel.
+CUDA only -- on other devices / unsupported widths it defers to the stock PyTorch ops of the wrapped modules
+(that is the same arithmetic, not a different implementation of the MSDeformAttn core).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ext
+
+
+class _AddDropoutLayerNorm(Function):
+    @staticmethod
+    def forward(ctx, x, branch, gamma, beta, p, training, eps):
+        m = ext.load()
+        keep = 1.0 - p
+        mask = None
+        if training and p > 0.0:
+            mask = torch.empty(x.shape, dtype=torch.bool, device=x.device).bernoulli_(keep)
+        y, s, mean, rstd = m.add_dropout_layernorm_forward(x, branch, mask, gamma, beta, keep, eps)
+        ctx.save_for_backward(s, mean, rstd, gamma, mask)
+        ctx.keep = keep
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        s, mean, rstd, gamma, mask = ctx.saved_tensors
+        dx, dbranch, dgamma, dbeta = ext.load().add_dropout_layernorm_backward(dy, s, mask, gamma, mean, rstd, ctx.keep)
+        return dx, dbranch, dgamma, dbeta, None, None, None
+
+
+def supported(x: torch.Tensor, norm: nn.LayerNorm) -> bool:
+    c = x.shape[-1]
+    return (x.is_cuda and x.dtype == torch.float32 and c % 128 == 0 and c <= 512
+            and norm.elementwise_affine and tuple(norm.normalized_shape) == (c,))
+
+
+def add_dropout_layernorm(x: torch.Tensor, branch: torch.Tensor, dropout: nn.Dropout, norm: nn.LayerNorm) -> torch.Tensor:
+    """``norm(x + dropout(branch))`` -- fused when the geometry allows, the module chain otherwise."""
+    if supported(x, norm) and branch.shape == x.shape:
+        return _AddDropoutLayerNorm.apply(x, branch, norm.weight, norm.bias, float(dropout.p),
+                                          bool(dropout.training), float(norm.eps))
+    return norm(x + dropout(branch))
