@@ -55,6 +55,8 @@ extern "C" {
 #define MSDA_E_TOO_LARGE (-3)  /* a per-sample slab exceeds 2^31-1 elements        */
 #define MSDA_E_LEVELS    (-4)  /* L > MSDA_B200_MAX_LEVELS                         */
 
+#define MSDA_E_UNSUPPORTED (-5) /* geometry outside a specialised entry point's domain */
+
 #define MSDA_B200_MAX_LEVELS 32
 
 int msda_b200_abi_version(void);
@@ -79,6 +81,16 @@ int msda_b200_backward_f64(const double* value, const int64_t* spatial_shapes,
                            double* grad_attn_weight,
                            int N, int S, int M, int D, int L, int Lq, int P, void* stream);
 
+/* ---- encoder self-attention (queries == pixels, Lq == S) with shared-memory staged value tiles -----------
+ * Same contract and same results as msda_b200_forward_f32, but the level sizes are ALSO given on the host
+ * (spatial_shapes_host, [L][2] int64 (H, W) in HOST memory): the grid is one CTA per 16x4 tile of queries per head.
+ * Returns MSDA_E_UNSUPPORTED (nothing launched) unless fp32, D == 32, L <= 8, L*P <= 64, Lq == S == sum(H*W),
+ * every H, W >= 2 and the buffers are 16-byte aligned -- callers then use msda_b200_forward_f32.
+ * No reference counterpart (the reference has a single kernel for every call site).                         */
+int msda_b200_forward_enc_tiled_f32(const float* value, const int64_t* spatial_shapes_host,
+                                    const float* sampling_loc, const float* attn_weight, float* output,
+                                    int N, int S, int M, int D, int L, int Lq, int P, void* stream);
+
 /* ---- host-buffer entry points (H2D + kernel + D2H inside the call; synchronous) -------- */
 int msda_b200_forward_host_f32(const float* value, const int64_t* spatial_shapes,
                                const float* sampling_loc, const float* attn_weight, float* output,
@@ -92,6 +104,8 @@ int msda_b200_backward_host_f32(const float* value, const int64_t* spatial_shape
 /* ---- introspection / tuning (not part of the reference surface) ------------------------ */
 /* Selects a kernel variant for experiments (0 = library default). Process-wide.            */
 void msda_b200_set_variant(int fwd_variant, int bwd_variant);
+/* 1 unless a non-default forward variant is forced (then the tiled encoder path is bypassed, for A/B timing) */
+int msda_b200_variant_allows_tiles(void);
 /* Number of kernel launches this library has enqueued since load (bench.py's gpu_launches). */
 uint64_t msda_b200_launch_count(void);
 

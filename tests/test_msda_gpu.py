@@ -345,3 +345,46 @@ def test_backward_determinism_of_loc_and_attn_grads(msda, dev):
     b = msda.ms_deform_attn_backward(value, shapes, loc, attn, gout, 64)
     assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])       # no atomics on these two
     torch.testing.assert_close(a[0], b[0], rtol=1e-5, atol=1e-5)     # grad_value: atomic order may differ
+
+
+# ----------------------------------------------------------------------------- tiled encoder forward
+TILE_CASES = {
+    "c1_enc": (1, 8, [(60, 80), (30, 40), (15, 20), (8, 10)], 4, "model"),
+    "c2_enc_n2": (2, 8, [(100, 167), (50, 84), (25, 42), (13, 21)], 4, "model"),
+    "odd_sizes": (1, 8, [(37, 53), (19, 27), (10, 14), (5, 7)], 4, "model"),
+    "wide_offsets": (1, 8, [(40, 56), (20, 28), (10, 14), (5, 7)], 4, "uniform"),       # boxes overflow -> global path
+    "two_levels_p8": (1, 8, [(24, 40), (12, 20)], 8, "model"),
+    "heads4": (1, 4, [(33, 47), (17, 24), (9, 12)], 4, "model"),
+    "l8_p4": (1, 8, [(20, 30), (10, 15), (5, 8), (3, 4)] * 2, 4, "model"),
+}
+
+
+@pytest.mark.parametrize("name", sorted(TILE_CASES))
+def test_tiled_encoder_forward_equals_general_kernel(msda, dev, name):
+    """Same taps, same accumulation order: the shared-memory tiled kernel must reproduce the general d32 kernel
+    bit for bit, and both must match the oracle."""
+    from oracle import msda_oracle
+    N, M, hw, P, dist = TILE_CASES[name]
+    g = torch.Generator().manual_seed(len(name))
+    shapes = torch.as_tensor(hw, dtype=torch.long)
+    L = len(hw)
+    S = int((shapes[:, 0] * shapes[:, 1]).sum())
+    value = torch.randn(N, S, M, 32, generator=g)
+    if dist == "uniform":
+        loc = torch.rand(N, S, M, L, P, 2, generator=g) * 1.2 - 0.1
+    else:
+        refs = []
+        for (h, w) in hw:
+            ys, xs = torch.meshgrid(torch.arange(h) + 0.5, torch.arange(w) + 0.5, indexing="ij")
+            refs.append(torch.stack([xs.reshape(-1) / w, ys.reshape(-1) / h], -1))
+        ref = torch.cat(refs, 0)[None, :, None, None, None, :]
+        off = torch.randn(N, S, M, L, P, 2, generator=g) * 2.5
+        loc = ref + off / shapes.flip(-1).float()[None, None, None, :, None, :]
+    attn = torch.softmax(torch.randn(N, S, M, L * P, generator=g), -1).view(N, S, M, L, P)
+    tv, ts, tl, ta = value.to(dev), shapes.to(dev), loc.to(dev), attn.to(dev)
+    flat_hw = [int(v) for pair in hw for v in pair]
+    tiled = msda.ms_deform_attn_forward_enc(tv, ts, tl, ta, flat_hw, 64)
+    general = msda.ms_deform_attn_forward(tv, ts, tl, ta, 64)
+    assert torch.equal(tiled, general)
+    ref_out = msda_oracle.msda_forward(value.numpy(), shapes.numpy(), loc.numpy(), attn.numpy())
+    np.testing.assert_allclose(tiled.cpu().numpy(), ref_out, **F32)

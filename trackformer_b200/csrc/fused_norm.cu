@@ -166,15 +166,29 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict_
   }
 }
 
-// dgamma[c] = sum_b partial[b][0][c], dbeta[c] = sum_b partial[b][1][c]   (fixed order -> deterministic)
-__global__ void ln_param_grad_finish_kernel(const float* __restrict__ partial, float* __restrict__ dgamma,
-                                            float* __restrict__ dbeta, int nblocks, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * C) return;
-  const int which = c / C, col = c - which * C;
+// dgamma[c] = sum_b partial[b][0][c], dbeta[c] = sum_b partial[b][1][c].  One warp per 32 output columns: lane = column
+// (coalesced 128-byte reads of each partial row), 8 warps of a CTA split the partial rows and combine through shared
+// memory in a fixed order -> deterministic.
+__global__ void __launch_bounds__(256)
+ln_param_grad_finish_kernel(const float* __restrict__ partial, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                            int nblocks, int C) {
+  __shared__ float acc_s[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;                 // column in [0, 2C)
   float acc = 0.f;
-  for (int b = 0; b < nblocks; ++b) acc += partial[(size_t(b) * 2 + which) * C + col];
-  (which == 0 ? dgamma : dbeta)[col] = acc;
+  if (c < 2 * C) {
+    const int which = c / C, col = c - which * C;
+    for (int b = w; b < nblocks; b += 8) acc += partial[(size_t(b) * 2 + which) * C + col];
+  }
+  acc_s[w][lane] = acc;
+  __syncthreads();
+  if (w == 0 && c < 2 * C) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += acc_s[k][lane];
+    const int which = c / C, col = c - which * C;
+    (which == 0 ? dgamma : dbeta)[col] = t;
+  }
 }
 
 int grid_for(int64_t rows) {
@@ -239,7 +253,7 @@ int tfb200_add_dropout_layernorm_bwd_f32(const float* dy, const float* s, const 
     default: return TFB200_E_SHAPE;   // the 48 KB static shared-memory reduction buffer bounds C at 512 here
   }
 #undef TFB200_BWD
-  ln_param_grad_finish_kernel<<<(2 * C + 255) / 256, 256, 0, st>>>(partial_ws, dgamma, dbeta, grid, C);
+  ln_param_grad_finish_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial_ws, dgamma, dbeta, grid, C);
   return int(cudaGetLastError());
 }
 

@@ -26,6 +26,7 @@
 #include "../../include/msda_b200.h"
 #include "msda_common.cuh"
 #include "msda_d32.cuh"
+#include "msda_tile.cuh"
 
 namespace msda {
 
@@ -384,6 +385,7 @@ const char* msda_b200_error_string(int code) {
     case MSDA_E_DIMS: return "msda_b200: non-positive dimension";
     case MSDA_E_TOO_LARGE: return "msda_b200: S*M*D exceeds 2^31-1 elements or D unsupported";
     case MSDA_E_LEVELS: return "msda_b200: too many levels";
+    case MSDA_E_UNSUPPORTED: return "msda_b200: geometry not supported by this specialised entry point";
     default: break;
   }
   if (code > 0) return cudaGetErrorString(cudaError_t(code));
@@ -396,6 +398,8 @@ void msda_b200_set_variant(int fwd_variant, int bwd_variant) {
 }
 
 uint64_t msda_b200_launch_count(void) { return g_launches.load(); }
+
+int msda_b200_variant_allows_tiles(void) { return g_fwd_variant.load() == 0 ? 1 : 0; }
 
 int msda_b200_forward_f32(const float* value, const int64_t* spatial_shapes, const float* sampling_loc,
                           const float* attn_weight, float* output, int N, int S, int M, int D, int L,
@@ -427,6 +431,45 @@ int msda_b200_backward_f64(const double* value, const int64_t* spatial_shapes, c
   return backward_impl<double>(value, spatial_shapes, sampling_loc, attn_weight, grad_output, grad_value,
                                grad_sampling_loc, grad_attn_weight, Dims{N, S, M, D, L, Lq, P},
                                cudaStream_t(stream));
+}
+
+int msda_b200_forward_enc_tiled_f32(const float* value, const int64_t* spatial_shapes_host, const float* sampling_loc,
+                                    const float* attn_weight, float* output, int N, int S, int M, int D, int L,
+                                    int Lq, int P, void* stream) {
+  const Dims d{N, S, M, D, L, Lq, P};
+  if (int rc = check_dims(d)) return rc;
+  if (!value || !spatial_shapes_host || !sampling_loc || !attn_weight || !output) return MSDA_E_NULLPTR;
+  if (D != 32 || L > kTileMaxLevels || L * P > kMaxLP || Lq != S || N < 1) return MSDA_E_UNSUPPORTED;
+  if (!aligned16(value) || !aligned16(sampling_loc) || !aligned16(attn_weight) || !aligned16(output))
+    return MSDA_E_UNSUPPORTED;
+  TileGeom g;
+  g.L = L; g.P = P; g.S = S; g.M = M;
+  int64_t acc = 0;
+  int tiles = 0;
+  for (int l = 0; l < L; ++l) {
+    const int64_t h = spatial_shapes_host[2 * l], w = spatial_shapes_host[2 * l + 1];
+    if (h < 2 || w < 2 || h > 65535 || w > 65535) return MSDA_E_UNSUPPORTED;
+    g.H[l] = int(h); g.W[l] = int(w); g.start[l] = int(acc);
+    g.tiles_x[l] = int((w + kTileX - 1) / kTileX);
+    g.tile_begin[l] = tiles;
+    tiles += g.tiles_x[l] * int((h + kTileY - 1) / kTileY);
+    acc += h * w;
+  }
+  g.tile_begin[L] = tiles;
+  if (acc != S) return MSDA_E_UNSUPPORTED;
+  const int64_t grid = int64_t(tiles) * M * N;
+  if (grid > INT32_MAX) return MSDA_E_UNSUPPORTED;
+  const size_t smem = fwd_tile_smem_bytes(L * P);
+  static std::atomic<bool> attr_set{false};
+  if (!attr_set.load()) {
+    cudaError_t e = cudaFuncSetAttribute(msda_fwd_enc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return int(e);
+    attr_set.store(true);
+  }
+  msda_fwd_enc_tile_kernel<<<unsigned(grid), kD32Threads, smem, cudaStream_t(stream)>>>(value, sampling_loc, attn_weight,
+                                                                                        output, g);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
 }
 
 int msda_b200_forward_host_f32(const float* value, const int64_t* spatial_shapes, const float* sampling_loc,

@@ -131,6 +131,26 @@ std::vector<at::Tensor> ms_deform_attn_backward(const at::Tensor& value, const a
   return {grad_value, grad_loc, grad_attn};
 }
 
+// Encoder self-attention (queries == pixels): tiled kernel when the geometry allows, the general kernel otherwise.
+// `hw` is the host copy of spatial_shapes ([H0, W0, H1, W1, ...]) the caller already has.
+at::Tensor ms_deform_attn_forward_enc(const at::Tensor& value, const at::Tensor& spatial_shapes,
+                                      const at::Tensor& sampling_loc, const at::Tensor& attn_weight,
+                                      const std::vector<int64_t>& hw, const int64_t im2col_step) {
+  const Geometry g = validate(value, spatial_shapes, sampling_loc, attn_weight, im2col_step);
+  if (value.scalar_type() == at::kFloat && int64_t(hw.size()) == 2 * int64_t(g.L) && msda_b200_variant_allows_tiles()) {
+    const c10::cuda::CUDAGuard guard(value.device());
+    const at::Tensor loc = sampling_loc.contiguous();
+    const at::Tensor attn = attn_weight.contiguous();
+    at::Tensor out = at::empty({g.N, g.Lq, int64_t(g.M) * g.D}, value.options());
+    const int rc = msda_b200_forward_enc_tiled_f32(value.data_ptr<float>(), hw.data(), loc.data_ptr<float>(),
+                                                   attn.data_ptr<float>(), out.data_ptr<float>(), g.N, g.S, g.M, g.D,
+                                                   g.L, g.Lq, g.P, c10::cuda::getCurrentCUDAStream().stream());
+    if (rc == 0) return out;
+    if (rc != MSDA_E_UNSUPPORTED) raise_on_error(rc, "ms_deform_attn_forward_enc");
+  }
+  return ms_deform_attn_forward(value, spatial_shapes, sampling_loc, attn_weight, im2col_step);
+}
+
 // ---- fused residual + dropout + LayerNorm (include/tfb200_fused.h) -------------------------------------------
 // forward: returns {y, s, mean, rstd}; keep_mask is an optional bool/uint8 tensor of x's shape
 std::vector<at::Tensor> add_dropout_layernorm_forward(const at::Tensor& x, const at::Tensor& branch,
@@ -197,6 +217,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("abi_version", []() { return msda_b200_abi_version(); });
   m.def("launch_count", []() { return msda_b200_launch_count(); });
   m.def("set_variant", [](int f, int b) { msda_b200_set_variant(f, b); });
+  m.def("ms_deform_attn_forward_enc", &ms_deform_attn_forward_enc);
   m.def("add_dropout_layernorm_forward", &add_dropout_layernorm_forward);
   m.def("add_dropout_layernorm_backward", &add_dropout_layernorm_backward);
 }

@@ -66,6 +66,33 @@ class MSDeformAttnFunction(Function):
         return g_value, None, g_loc, g_attn, None
 
 
+class MSDeformAttnEncFunction(Function):
+    """Encoder self-attention variant (queries are the pixels, ``Lq == S``): the forward may run the
+    shared-memory tiled kernel, which needs the level sizes on the host -- taken from the ``_hw_list`` the
+    transformer attaches to ``value_spatial_shapes``.  Results and the backward are those of
+    :class:`MSDeformAttnFunction`; geometries the tiled kernel does not cover fall through to the general
+    kernel inside the extension (still CUDA -- there is no CPU path)."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, sampling_locations, attention_weights, im2col_step):
+        msda = ext.load()
+        ctx.im2col_step = int(im2col_step)
+        hw = [int(v) for pair in value_spatial_shapes._hw_list for v in pair]
+        sink = _TIMING_SINK
+        if sink is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        out = msda.ms_deform_attn_forward_enc(value, value_spatial_shapes, sampling_locations, attention_weights,
+                                              hw, ctx.im2col_step)
+        if sink is not None:
+            e1.record()
+            sink.append(("fwd", _dims(value, sampling_locations), e0, e1))
+        ctx.save_for_backward(value, value_spatial_shapes, sampling_locations, attention_weights)
+        return out
+
+    backward = MSDeformAttnFunction.backward
+
+
 def ms_deform_attn(value: torch.Tensor, spatial_shapes: torch.Tensor, sampling_locations: torch.Tensor,
                    attention_weights: torch.Tensor, im2col_step: int = 64) -> torch.Tensor:
     """Functional form: ``[N,S,M,D] x [L,2] x [N,Lq,M,L,P,2] x [N,Lq,M,L,P] -> [N,Lq,M*D]``."""

@@ -18,7 +18,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .msda_function import MSDeformAttnFunction
+from .msda_function import MSDeformAttnEncFunction, MSDeformAttnFunction
 
 # the 8 compass directions the reference seeds the per-head offset bias with (ms_deform_attn.py:36)
 _COMPASS = ((-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 1), (1, -1), (1, 0), (1, 1))
@@ -97,5 +97,9 @@ class MSDeformAttn(nn.Module):
             raise ValueError(
                 "Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
 
-        out = MSDeformAttnFunction.apply(value, input_spatial_shapes, locations, attn, self.im2col_step)
+        if hw is not None and len_q == len_in and value.is_cuda:
+            # encoder self-attention: queries are the pixels -> shared-memory tiled forward kernel
+            out = MSDeformAttnEncFunction.apply(value, input_spatial_shapes, locations, attn, self.im2col_step)
+        else:
+            out = MSDeformAttnFunction.apply(value, input_spatial_shapes, locations, attn, self.im2col_step)
         return self.output_proj(out)

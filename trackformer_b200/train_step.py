@@ -52,6 +52,9 @@ class TrainStep:
         self.criterion = criterion
         self.max_norm = max_norm
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        prepare = getattr(getattr(model, "backbone", [None])[0], "prepare", None)
+        if prepare is not None:
+            prepare()                                   # final parameter memory formats before gradient views exist
         self.params: List[nn.Parameter] = [p for p in model.parameters() if p.requires_grad]
         self.core = _DetectorCore(model)
         self.g_fwd = self.g_bwd = None
@@ -62,7 +65,12 @@ class TrainStep:
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         ofs = 0
         for p in self.params:
-            p.grad = self.flat_grad[ofs:ofs + p.numel()].view_as(p)
+            chunk = self.flat_grad[ofs:ofs + p.numel()]
+            if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
+                o, i, kh, kw = p.shape                  # NHWC filter: the gradient view gets the same strides
+                p.grad = chunk.view(o, kh, kw, i).permute(0, 3, 1, 2)
+            else:
+                p.grad = chunk.view_as(p)
             ofs += p.numel()
         self.optimizer = optimizer_factory(self.params) if optimizer_factory is not None else None
         if use_graphs:
