@@ -39,6 +39,18 @@ int tfb200_add_dropout_layernorm_bwd_f32(const float* dy, const float* s, const 
                                          float* dbranch, float* dgamma, float* dbeta, float* partial_ws,
                                          int64_t rows, int C, float keep_prob, void* stream);
 
+/* out[c] = sum_r x[r][c]  (bias gradient of a Linear over a long token axis); C % 128 == 0, C <= 1024;
+ * partial_ws: [tfb200_ln_partial_ctas(rows)][C] fp32.  Deterministic (fixed summation order).                      */
+int tfb200_colsum_f32(const float* x, float* out, float* partial_ws, int64_t rows, int C, void* stream);
+
+/* h = dropout(relu(a)) in one pass (FFN hidden activation, deformable_transformer.py:283,359).  Inverted dropout with a
+ * counter-based keep decision hashed from (*seed_dev, element index): no mask tensor.  backward: grad_a from grad_h and
+ * h alone (h > 0 <=> a > 0 and kept).  n % 4 == 0.  training == 0: plain ReLU.                                        */
+int tfb200_relu_dropout_fwd_f32(const float* a, float* h, const int64_t* seed_dev, int64_t n, float keep_prob,
+                                int training, void* stream);
+int tfb200_relu_dropout_bwd_f32(const float* grad_h, const float* h, float* grad_a, int64_t n, float keep_prob,
+                                int training, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,3 +76,51 @@ def test_module_level_wrapper(dev):
     x288 = torch.randn(3, 5, 288, device=dev)
     assert not supported(x288, norm288)
     torch.testing.assert_close(add_dropout_layernorm(x288, x288, drop.eval(), norm288), norm288(2 * x288))
+
+
+def test_colsum_and_fused_linear(dev):
+    from trackformer_b200 import ext
+    from trackformer_b200.fused_linear import linear
+    m = ext.load()
+    for rows, c in ((22223, 256), (5000, 384), (4097, 1024), (3, 128)):
+        x = torch.randn(rows, c, device=dev)
+        got = m.colsum(x)
+        torch.testing.assert_close(got, x.double().sum(0).float(), rtol=1e-4, atol=1e-3)
+        assert torch.equal(got, m.colsum(x))                               # deterministic
+    x = torch.randn(1, 6000, 256, device=dev, requires_grad=True)
+    w = torch.randn(384, 256, device=dev, requires_grad=True)
+    b = torch.randn(384, device=dev, requires_grad=True)
+    y = linear(x, w, b)
+    y_ref = torch.nn.functional.linear(x, w, b)
+    torch.testing.assert_close(y, y_ref)
+    gy = torch.randn_like(y)
+    g = torch.autograd.grad(y, (x, w, b), gy)
+    r = torch.autograd.grad(y_ref, (x, w, b), gy)
+    for a_, b_ in zip(g, r):
+        torch.testing.assert_close(a_, b_, rtol=1e-4, atol=1e-3)
+
+
+def test_relu_dropout(dev):
+    from trackformer_b200.fused_linear import relu_dropout
+    a = torch.randn(1, 22223, 1024, device=dev, requires_grad=True)
+    drop = torch.nn.Dropout(0.1).eval()
+    h = relu_dropout(a, drop)
+    torch.testing.assert_close(h, torch.relu(a))
+    g, = torch.autograd.grad(h, a, torch.ones_like(h))
+    torch.testing.assert_close(g, (a > 0).float())
+    drop.train()
+    torch.manual_seed(0)
+    h1 = relu_dropout(a, drop)
+    h2 = relu_dropout(a, drop)
+    pos = a > 0
+    kept = (h1 > 0)
+    assert not (kept & ~pos).any()                                         # never resurrects a negative input
+    frac = float(kept[pos].float().mean())
+    assert 0.895 < frac < 0.905                                            # keep probability 0.9
+    torch.testing.assert_close(h1[kept], (a[kept] / 0.9))                  # inverted-dropout scaling
+    assert not torch.equal(h1 > 0, h2 > 0)                                 # a fresh mask every call
+    # per-column / per-row keep rates are flat (no visible structure in the hash)
+    col = kept.float().sum(1) / pos.float().sum(1).clamp(min=1)
+    assert float((col - 0.9).abs().max()) < 0.02
+    g1, = torch.autograd.grad(h1, a, torch.ones_like(h1))
+    torch.testing.assert_close(g1, kept.float() / 0.9)

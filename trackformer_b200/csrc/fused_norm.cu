@@ -166,28 +166,97 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict_
   }
 }
 
-// dgamma[c] = sum_b partial[b][0][c], dbeta[c] = sum_b partial[b][1][c].  One warp per 32 output columns: lane = column
-// (coalesced 128-byte reads of each partial row), 8 warps of a CTA split the partial rows and combine through shared
-// memory in a fixed order -> deterministic.
+// out[c] = sum_b partial[b][c] for c < width, written to out0 (c < split) / out1 (c >= split).  One warp per 32
+// output columns: lane = column (coalesced 128-byte reads of each partial row), the 8 warps of a CTA split the partial
+// rows and combine through shared memory in a fixed order -> deterministic.
 __global__ void __launch_bounds__(256)
-ln_param_grad_finish_kernel(const float* __restrict__ partial, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                            int nblocks, int C) {
+column_partials_finish_kernel(const float* __restrict__ partial, float* __restrict__ out0, float* __restrict__ out1,
+                              int nblocks, int width, int split) {
   __shared__ float acc_s[8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;                 // column in [0, 2C)
+  const int c = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  if (c < 2 * C) {
-    const int which = c / C, col = c - which * C;
-    for (int b = w; b < nblocks; b += 8) acc += partial[(size_t(b) * 2 + which) * C + col];
-  }
+  if (c < width)
+    for (int b = w; b < nblocks; b += 8) acc += partial[size_t(b) * width + c];
   acc_s[w][lane] = acc;
   __syncthreads();
-  if (w == 0 && c < 2 * C) {
+  if (w == 0 && c < width) {
     float t = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) t += acc_s[k][lane];
-    const int which = c / C, col = c - which * C;
-    (which == 0 ? dgamma : dbeta)[col] = t;
+    if (c < split) out0[c] = t; else out1[c - split] = t;
+  }
+}
+
+// Column sums of a [rows, C] matrix (bias gradients of the big encoder Linears): same row-per-warp streaming as the
+// LayerNorm backward, partial[blockIdx][c].
+template <int PACKS>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+colsum_kernel(const float* __restrict__ x, float* __restrict__ partial, int64_t rows) {
+  constexpr int C = PACKS * 128;
+  __shared__ float red[kWarpsPerCta][C];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t warp = int64_t(blockIdx.x) * kWarpsPerCta + wid;
+  const int64_t nwarps = int64_t(gridDim.x) * kWarpsPerCta;
+  float4 acc[PACKS];
+#pragma unroll
+  for (int k = 0; k < PACKS; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = warp; r < rows; r += nwarps) {
+#pragma unroll
+    for (int k = 0; k < PACKS; ++k) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C) + k * 32 + lane);
+      acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < PACKS; ++k) reinterpret_cast<float4*>(&red[wid][0])[k * 32 + lane] = acc[k];
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += kWarpsPerCta * 32) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarpsPerCta; ++w) t += red[w][c];
+    partial[size_t(blockIdx.x) * C + c] = t;
+  }
+}
+
+// Fused ReLU + inverted dropout for the FFN hidden activation, mask-free: the keep decision is a counter-based hash
+// of (seed, element index); the backward needs no mask because h > 0 <=> (a > 0 and kept).
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool keep_elem(uint64_t seed, uint64_t idx, uint32_t keep_thresh) {
+  const uint32_t h = mix32(uint32_t(idx) ^ mix32(uint32_t(idx >> 32) + uint32_t(seed)) ^ uint32_t(seed >> 32) * 0x9e3779b9u);
+  return h < keep_thresh;
+}
+
+__global__ void __launch_bounds__(256)
+relu_dropout_fwd_kernel(const float* __restrict__ a, float* __restrict__ h, const int64_t* __restrict__ seed_ptr,
+                        int64_t n4, float inv_keep, uint32_t keep_thresh, int training) {
+  const uint64_t seed = training ? uint64_t(__ldg(seed_ptr)) : 0;
+  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < n4; i += int64_t(gridDim.x) * 256) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(a) + i);
+    float4 o;
+    if (training) {
+      o.x = (v.x > 0.f && keep_elem(seed, 4 * i + 0, keep_thresh)) ? v.x * inv_keep : 0.f;
+      o.y = (v.y > 0.f && keep_elem(seed, 4 * i + 1, keep_thresh)) ? v.y * inv_keep : 0.f;
+      o.z = (v.z > 0.f && keep_elem(seed, 4 * i + 2, keep_thresh)) ? v.z * inv_keep : 0.f;
+      o.w = (v.w > 0.f && keep_elem(seed, 4 * i + 3, keep_thresh)) ? v.w * inv_keep : 0.f;
+    } else {
+      o = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+    }
+    reinterpret_cast<float4*>(h)[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+relu_dropout_bwd_kernel(const float* __restrict__ gh, const float* __restrict__ h, float* __restrict__ ga, int64_t n4,
+                        float inv_keep) {
+  for (int64_t i = int64_t(blockIdx.x) * 256 + threadIdx.x; i < n4; i += int64_t(gridDim.x) * 256) {
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gh) + i);
+    const float4 o = __ldg(reinterpret_cast<const float4*>(h) + i);
+    reinterpret_cast<float4*>(ga)[i] = make_float4(o.x > 0.f ? g.x * inv_keep : 0.f, o.y > 0.f ? g.y * inv_keep : 0.f,
+                                                   o.z > 0.f ? g.z * inv_keep : 0.f, o.w > 0.f ? g.w * inv_keep : 0.f);
   }
 }
 
@@ -253,7 +322,55 @@ int tfb200_add_dropout_layernorm_bwd_f32(const float* dy, const float* s, const 
     default: return TFB200_E_SHAPE;   // the 48 KB static shared-memory reduction buffer bounds C at 512 here
   }
 #undef TFB200_BWD
-  ln_param_grad_finish_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial_ws, dgamma, dbeta, grid, C);
+  column_partials_finish_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial_ws, dgamma, dbeta, grid, 2 * C, C);
+  return int(cudaGetLastError());
+}
+
+int tfb200_colsum_f32(const float* x, float* out, float* partial_ws, int64_t rows, int C, void* stream) {
+  if (!x || !out || !partial_ws) return TFB200_E_NULLPTR;
+  if (rows < 0 || C <= 0 || C % 128 != 0 || C > 128 * kMaxPacks) return TFB200_E_SHAPE;
+  cudaStream_t st = cudaStream_t(stream);
+  if (rows == 0) {
+    cudaMemsetAsync(out, 0, sizeof(float) * C, st);
+    return int(cudaGetLastError());
+  }
+  const int grid = grid_for(rows);
+#define TFB200_CS(P) colsum_kernel<P><<<grid, kWarpsPerCta * 32, 0, st>>>(x, partial_ws, rows)
+  switch (C / 128) {
+    case 1: TFB200_CS(1); break;
+    case 2: TFB200_CS(2); break;
+    case 3: TFB200_CS(3); break;
+    case 4: TFB200_CS(4); break;
+    case 8: TFB200_CS(8); break;
+    default: return TFB200_E_SHAPE;
+  }
+#undef TFB200_CS
+  column_partials_finish_kernel<<<(C + 31) / 32, 256, 0, st>>>(partial_ws, out, out, grid, C, C);
+  return int(cudaGetLastError());
+}
+
+int tfb200_relu_dropout_fwd_f32(const float* a, float* h, const int64_t* seed_dev, int64_t n, float keep_prob,
+                                int training, void* stream) {
+  if (!a || !h || (training && !seed_dev)) return TFB200_E_NULLPTR;
+  if (n < 0 || n % 4 != 0) return TFB200_E_SHAPE;
+  if (n == 0) return 0;
+  const int64_t n4 = n / 4;
+  const int grid = int(n4 / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  const double t = double(keep_prob) * 4294967296.0;
+  const uint32_t thresh = t >= 4294967295.0 ? 0xffffffffu : uint32_t(t);
+  relu_dropout_fwd_kernel<<<grid, 256, 0, cudaStream_t(stream)>>>(a, h, seed_dev, n4, training ? 1.f / keep_prob : 1.f,
+                                                                  thresh, training);
+  return int(cudaGetLastError());
+}
+
+int tfb200_relu_dropout_bwd_f32(const float* grad_h, const float* h, float* grad_a, int64_t n, float keep_prob,
+                                int training, void* stream) {
+  if (!grad_h || !h || !grad_a) return TFB200_E_NULLPTR;
+  if (n < 0 || n % 4 != 0) return TFB200_E_SHAPE;
+  if (n == 0) return 0;
+  const int64_t n4 = n / 4;
+  const int grid = int(n4 / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
+  relu_dropout_bwd_kernel<<<grid, 256, 0, cudaStream_t(stream)>>>(grad_h, h, grad_a, n4, training ? 1.f / keep_prob : 1.f);
   return int(cudaGetLastError());
 }
 

@@ -209,6 +209,46 @@ std::vector<at::Tensor> add_dropout_layernorm_backward(const at::Tensor& dy, con
   return {dx, db, dgamma, dbeta};
 }
 
+at::Tensor colsum(const at::Tensor& x) {
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kFloat && x.dim() >= 2, "colsum: fp32 CUDA matrix required");
+  const at::Tensor xc = x.contiguous();
+  const int64_t C = xc.size(-1), rows = xc.numel() / C;
+  const c10::cuda::CUDAGuard guard(x.device());
+  at::Tensor out = at::empty({C}, xc.options());
+  at::Tensor ws = at::empty({tfb200_ln_partial_ctas(rows), C}, xc.options());
+  const int rc = tfb200_colsum_f32(xc.data_ptr<float>(), out.data_ptr<float>(), ws.data_ptr<float>(), rows, int(C),
+                                   c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "colsum failed (code ", rc, "): C must be a multiple of 128 and <= 1024");
+  return out;
+}
+
+at::Tensor relu_dropout_forward(const at::Tensor& a, const c10::optional<at::Tensor>& seed, double keep_prob, bool training) {
+  TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kFloat, "relu_dropout: fp32 CUDA tensor required");
+  const at::Tensor ac = a.contiguous();
+  const c10::cuda::CUDAGuard guard(a.device());
+  at::Tensor h = at::empty_like(ac);
+  const int64_t* sp = nullptr;
+  if (training) {
+    TORCH_CHECK(seed.has_value() && seed->is_cuda() && seed->scalar_type() == at::kLong && seed->numel() >= 1,
+                "relu_dropout: training mode needs an int64 CUDA seed tensor");
+    sp = seed->data_ptr<int64_t>();
+  }
+  const int rc = tfb200_relu_dropout_fwd_f32(ac.data_ptr<float>(), h.data_ptr<float>(), sp, ac.numel(), float(keep_prob),
+                                             training ? 1 : 0, c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "relu_dropout_forward failed (code ", rc, ")");
+  return h;
+}
+
+at::Tensor relu_dropout_backward(const at::Tensor& grad_h, const at::Tensor& h, double keep_prob, bool training) {
+  const at::Tensor g = grad_h.contiguous();
+  const c10::cuda::CUDAGuard guard(h.device());
+  at::Tensor ga = at::empty_like(h);
+  const int rc = tfb200_relu_dropout_bwd_f32(g.data_ptr<float>(), h.data_ptr<float>(), ga.data_ptr<float>(), h.numel(),
+                                             float(keep_prob), training ? 1 : 0, c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "relu_dropout_backward failed (code ", rc, ")");
+  return ga;
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200 (sm_100a) multi-scale deformable attention; drop-in for the reference extension";
   m.def("ms_deform_attn_forward", &ms_deform_attn_forward, "ms_deform_attn_forward");
@@ -220,4 +260,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ms_deform_attn_forward_enc", &ms_deform_attn_forward_enc);
   m.def("add_dropout_layernorm_forward", &add_dropout_layernorm_forward);
   m.def("add_dropout_layernorm_backward", &add_dropout_layernorm_backward);
+  m.def("colsum", &colsum);
+  m.def("relu_dropout_forward", &relu_dropout_forward);
+  m.def("relu_dropout_backward", &relu_dropout_backward);
 }

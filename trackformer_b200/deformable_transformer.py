@@ -20,6 +20,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .fused_linear import linear as fused_linear, relu_dropout
 from .fused_norm import add_dropout_layernorm
 from .msda_module import MSDeformAttn
 from .util import inverse_sigmoid
@@ -57,7 +58,9 @@ class DeformableTransformerEncoderLayer(nn.Module):
     with_pos_embed = staticmethod(_add_pos)
 
     def forward_ffn(self, src):
-        ff = self.linear2(self.dropout2(self.activation(self.linear1(src))))
+        a = fused_linear(src, self.linear1.weight, self.linear1.bias)
+        h = relu_dropout(a, self.dropout2) if self.activation is F.relu else self.dropout2(self.activation(a))
+        ff = fused_linear(h, self.linear2.weight, self.linear2.bias)
         return add_dropout_layernorm(src, ff, self.dropout3, self.norm2)
 
     def forward(self, src, pos, reference_points, spatial_shapes, padding_mask=None):

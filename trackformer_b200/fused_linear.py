@@ -1,0 +1,81 @@
+"""Linear layers and the FFN activation of the encoder with fused sm_100a epilogue kernels.
+
+* ``linear(x, weight, bias)`` -- ``F.linear`` whose backward computes the bias gradient with the library's
+  streaming column-sum kernel (one HBM-bound pass, deterministic) instead of PyTorch's generic reduction
+  (33-40 us per [22223, 256..1024] call, 36 calls per C2 step).  The two GEMMs stay on cuBLAS tensor cores.
+* ``relu_dropout(a, dropout)`` -- ``dropout(relu(a))`` in one pass, mask-free (the keep decision is a hash of a
+  per-call seed and the element index; the backward reads the output only).
+
+Both defer to the stock PyTorch ops on CPU tensors and for shapes outside the kernels' domain -- the same arithmetic,
+not an alternative implementation of the MSDeformAttn core.  Reference call sites:
+src/trackformer/models/deformable_transformer.py:282-286 (FFN), ops/modules/ms_deform_attn.py:64-88 (projections).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ext
+
+_MIN_ROWS = 2048          # below this the generic reduction is launch-bound anyway
+
+
+class _LinearColsum(Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        return F.linear(x, weight, bias)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        gy2 = gy.reshape(-1, gy.shape[-1])
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = (gy2 @ weight).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            gw = gy2.t() @ x.reshape(-1, x.shape[-1])
+        if ctx.needs_input_grad[2]:
+            gb = ext.load().colsum(gy2)
+        return gx, gw, gb
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    rows = x.numel() // x.shape[-1]
+    c_out = weight.shape[0]
+    if (x.is_cuda and x.dtype == torch.float32 and bias is not None and rows >= _MIN_ROWS
+            and c_out % 128 == 0 and c_out <= 1024 and torch.is_grad_enabled()):
+        return _LinearColsum.apply(x, weight, bias)
+    return F.linear(x, weight, bias)
+
+
+class _ReluDropout(Function):
+    @staticmethod
+    def forward(ctx, a, p, training):
+        m = ext.load()
+        keep = 1.0 - p
+        seed = None
+        if training:
+            seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=a.device)
+        h = m.relu_dropout_forward(a, seed, keep, training)
+        ctx.save_for_backward(h)
+        ctx.keep, ctx.training = keep, training
+        return h
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gh):
+        (h,) = ctx.saved_tensors
+        return ext.load().relu_dropout_backward(gh, h, ctx.keep, ctx.training), None, None
+
+
+def relu_dropout(a: torch.Tensor, dropout: nn.Dropout) -> torch.Tensor:
+    """``dropout(relu(a))``."""
+    if a.is_cuda and a.dtype == torch.float32 and a.numel() % 4 == 0 and a.numel() >= 4 * _MIN_ROWS:
+        training = bool(dropout.training and dropout.p > 0.0)
+        return _ReluDropout.apply(a, float(dropout.p), training)
+    return dropout(F.relu(a))

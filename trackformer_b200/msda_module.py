@@ -14,11 +14,16 @@ Host-side differences (results identical up to fp32 rounding):
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .fused_linear import linear as fused_linear
 from .msda_function import MSDeformAttnEncFunction, MSDeformAttnFunction
+
+_TILED_ENC = os.environ.get("TFB200_TILED_ENC", "0") == "1"
 
 # the 8 compass directions the reference seeds the per-head offset bias with (ms_deform_attn.py:36)
 _COMPASS = ((-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 1), (1, -1), (1, 0), (1, 1))
@@ -72,7 +77,7 @@ class MSDeformAttn(nn.Module):
         else:                                                       # reference behaviour: device reduction + sync
             assert int((input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum()) == len_in
 
-        value = self.value_proj(input_flatten)
+        value = fused_linear(input_flatten, self.value_proj.weight, self.value_proj.bias)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], 0.0)
         value = value.view(n, len_in, m, self.d_model // m)
@@ -81,7 +86,7 @@ class MSDeformAttn(nn.Module):
         n_off = m * lv * pt * 2
         w_cat = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
         b_cat = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
-        proj = F.linear(query, w_cat, b_cat)
+        proj = fused_linear(query, w_cat, b_cat)
         offsets = proj[..., :n_off].reshape(n, len_q, m, lv, pt, 2)
         attn = F.softmax(proj[..., n_off:].reshape(n, len_q, m, lv * pt), -1).view(n, len_q, m, lv, pt)
         if query_attn_mask is not None:
@@ -97,9 +102,10 @@ class MSDeformAttn(nn.Module):
             raise ValueError(
                 "Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
 
-        if hw is not None and len_q == len_in and value.is_cuda:
-            # encoder self-attention: queries are the pixels -> shared-memory tiled forward kernel
+        if _TILED_ENC and hw is not None and len_q == len_in and value.is_cuda:
+            # encoder self-attention: queries are the pixels -> shared-memory tiled forward kernel (opt-in:
+            # bit-identical but currently slower than the direct kernel)
             out = MSDeformAttnEncFunction.apply(value, input_spatial_shapes, locations, attn, self.im2col_step)
         else:
             out = MSDeformAttnFunction.apply(value, input_spatial_shapes, locations, attn, self.im2col_step)
-        return self.output_proj(out)
+        return fused_linear(out, self.output_proj.weight, self.output_proj.bias)
