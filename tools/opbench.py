@@ -120,6 +120,7 @@ def main():
     ap.add_argument("--bwd-variants", default="0")
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--once", action="store_true")
+    ap.add_argument("--ref", action="store_true", help="also time the reference's own CUDA kernels (oracle/_ref)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "opbench.json"))
     args = ap.parse_args()
 
@@ -163,6 +164,31 @@ def main():
                 results.append(r)
                 print(json.dumps(r), flush=True)
     msda.set_variant(0, 0)
+    # "the kernel to beat": the reference's own CUDA kernels compiled for sm_100a (oracle/_ref, test infrastructure)
+    try:
+        from oracle import refcuda
+        have_ref = refcuda.available() and not args.once and args.ref
+    except Exception:
+        have_ref = False
+    if have_ref:
+        for name in args.cases.split(","):
+            (value, shapes, loc, attn, gout), dims, fwd_b, bwd_b = make_case(name, dev)
+            lib = refcuda._load()
+            ws = torch.empty(lib.refcuda_ws_bytes(dims["N"], dims["M"], dims["D"], dims["L"], dims["Lq"], dims["P"], 4),
+                             dtype=torch.uint8, device=dev)
+            for kind, fn, nbytes in (("fwd", lambda: refcuda.forward(value, shapes, loc, attn, ws), fwd_b),
+                                     ("bwd", lambda: refcuda.backward(value, shapes, loc, attn, gout, ws), bwd_b)):
+                for _ in range(3):
+                    fn()
+                cold, _ = time_kernel(fn, max(5, args.iters // 3), flush, dev)
+                warm, _ = time_kernel(fn, max(5, args.iters // 3), None, dev)
+                r = dict(case=name, kind=kind, variant="reference_cuda", **dims, alg_bytes=nbytes, cold_us=round(cold, 2),
+                         warm_us=round(warm, 2), cold_gbs=round(nbytes / cold / 1e3, 1), warm_gbs=round(nbytes / warm / 1e3, 1),
+                         frac_cold=round(nbytes / cold / 1e3 / peak, 4), frac_warm=round(nbytes / warm / 1e3 / peak, 4),
+                         peak_gbs=peak, peak_src=peak_src)
+                results.append(r)
+                print(json.dumps(r), flush=True)
+            del ws
     if not args.once:
         os.makedirs(os.path.dirname(args.out), exist_ok=True)
         json.dump(results, open(args.out, "w"), indent=1)
