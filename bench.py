@@ -322,6 +322,21 @@ def main():
                     "note": "algorithmic (compulsory) bytes / CUDA-event launch time, every launch bracketed by events in an "
                             "eager replay of the timed step (graph replays cannot host per-kernel events); "
                             "the gather itself is L1-wavefront bound, see DESIGN.md"}
+    # second yardstick: the measured L1-data-stage ceiling for gather-shaped LDG.128 requests (tools/l1_gather_peak.py)
+    l1_roofline = None
+    l1_path = os.path.join(ROOT, "profiles", "l1_gather_peak.json")
+    if per_kernel and os.path.exists(l1_path):
+        l1_peak = json.load(open(l1_path))["l2_resident_22.8MB"]["gbs"]
+        l1_roofline = {"peak_gbs": l1_peak, "peak_source": "profiles/l1_gather_peak.json (gather-shaped LDG.128 probe, "
+                       "22.8 MB table = a C2 frame's value)", "kernels": {}}
+        for r in per_kernel:
+            n, s_, m, d, l, lq, p = r["dims_N_S_M_D_L_Lq_P"]
+            gathered = n * lq * m * l * p * 4 * d * 4                       # corner rows read through L1
+            if r["kernel"].startswith("msda_bwd"):
+                gathered *= 2                                                # + the same rows as vector reductions
+            gbs = gathered / r["mean_us"] / 1e3
+            l1_roofline["kernels"][r["kernel"]] = {"gathered_bytes": gathered, "achieved_gbs": round(gbs, 1),
+                                                   "frac": round(gbs / l1_peak, 4)}
     msda_ms = sum(r["total_ms_per_step"] for r in per_kernel)
 
     cpu_baseline = None
@@ -356,6 +371,7 @@ def main():
         "gpu_launches": int(launches) * world,
         "clocks": clocks,
         "roofline": roofline,
+        "l1_roofline": l1_roofline,
         "msda_kernels": per_kernel,
         "msda_ms_per_step": round(msda_ms, 4),
         "cpu_baseline": cpu_baseline,

@@ -106,6 +106,10 @@ int msda_b200_backward_host_f32(const float* value, const int64_t* spatial_shape
 void msda_b200_set_variant(int fwd_variant, int bwd_variant);
 /* 1 unless a non-default forward variant is forced (then the tiled encoder path is bypassed, for A/B timing) */
 int msda_b200_variant_allows_tiles(void);
+/* Measurement aid: `ctas` CTAs of 256 threads each issue `iters` gather-shaped LDG.128 requests (4 x 128-byte rows
+ * per warp request, rows drawn pseudo-randomly from table[rows][32] floats).  Bytes moved = ctas*256*iters*16.
+ * Used by tools/l1_gather_peak.py to measure the L1-data-stage ceiling the gather kernels are compared against.   */
+int msda_b200_l1_gather_probe(const float* table, float* sink, int64_t rows, int iters, int ctas, void* stream);
 /* Number of kernel launches this library has enqueued since load (bench.py's gpu_launches). */
 uint64_t msda_b200_launch_count(void);
 

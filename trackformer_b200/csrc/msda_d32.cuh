@@ -101,8 +101,8 @@ __device__ __forceinline__ void fma4(float4& acc, float w, const float4& v) {
 // Forward
 // ------------------------------------------------------------------------------------------------
 // STRIDE_CT: M*D in elements when known at compile time (256 for the shipped M = 8), else 0.
-template <int STRIDE_CT>
-__global__ void __launch_bounds__(kD32Threads)
+template <int STRIDE_CT, int UNROLL = 4, int MINB = 1>
+__global__ void __launch_bounds__(kD32Threads, MINB)
 msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                     const float* __restrict__ loc, const float* __restrict__ attn,
                     float* __restrict__ out, int S, int M, int L, int Lq, int P, uint32_t groups, int iters) {
@@ -169,7 +169,7 @@ msda_fwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__
         const int H = lv.H[l], W = lv.W[l];
         if (H >= 2 && W >= 2) {
           const int rowpitch = W * stride;
-#pragma unroll 4
+#pragma unroll UNROLL
           for (int p = 0; p < P; ++p) {
             const int s = l * P + p;
             const float4 w = rw[s];

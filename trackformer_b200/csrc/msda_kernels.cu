@@ -264,12 +264,24 @@ static int forward_impl(const T* value, const int64_t* shapes, const T* loc, con
     if (variant != 1 && vec_ok && d.D == 32 && LP <= kMaxLP && aligned16(loc) && aligned16(attn) &&
         groups < (int64_t(1) << 31)) {
       const int64_t ctas = (groups + kGroupsPerCta - 1) / kGroupsPerCta;
-      const int iters = variant >= 2 ? variant - 1 : pick_iters(ctas);
+      // variant = 10 * tuning + iters_code: iters_code >= 2 forces iters = code - 1; tuning picks (unroll, min CTAs/SM)
+      const int tuning = variant / 10, icode = variant % 10;
+      const int iters = icode >= 2 ? icode - 1 : pick_iters(ctas);
       const unsigned grid = unsigned((ctas + iters - 1) / iters);
       const size_t smem = fwd_d32_smem_bytes(LP);
-      if (d.M == 8)
-        msda_fwd_d32_kernel<256><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, out, d.S, d.M, d.L, d.Lq,
-                                                                  d.P, uint32_t(groups), iters);
+#define MSDA_FWD_D32(U, B)                                                                                          \
+  msda_fwd_d32_kernel<256, U, B><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, out, d.S, d.M, d.L, d.Lq, \
+                                                                  d.P, uint32_t(groups), iters)
+      if (d.M == 8 && tuning == 1) MSDA_FWD_D32(2, 5);
+      else if (d.M == 8 && tuning == 2) MSDA_FWD_D32(2, 6);
+      else if (d.M == 8 && tuning == 3) MSDA_FWD_D32(4, 5);
+      else if (d.M == 8 && tuning == 4) MSDA_FWD_D32(1, 6);
+      else if (d.M == 8 && tuning == 5) MSDA_FWD_D32(4, 3);
+      else if (d.M == 8 && tuning == 6) MSDA_FWD_D32(4, 4);
+      else if (d.M == 8 && tuning == 7) MSDA_FWD_D32(8, 2);
+      else if (d.M == 8 && tuning == 8) MSDA_FWD_D32(4, 1);
+      else if (d.M == 8) MSDA_FWD_D32(4, 4);          // measured best overall (profiles/): 64 registers, 4 CTAs/SM
+#undef MSDA_FWD_D32
       else
         msda_fwd_d32_kernel<0><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, out, d.S, d.M, d.L, d.Lq,
                                                                 d.P, uint32_t(groups), iters);
@@ -358,6 +370,25 @@ static int backward_impl(const T* value, const int64_t* shapes, const T* loc, co
   return int(cudaGetLastError());
 }
 
+// ---- measurement aid: what can the L1 data stage deliver for THIS access pattern? -------------------------------
+// Every warp issues LDG.128 requests shaped exactly like the gather's: 4 groups x 8 lanes, each group reading one
+// 128-byte row chosen pseudo-randomly from a table of `rows` rows (table small => L1 hits; 22.8 MB => L2 hits).
+// Nothing else happens, so bytes/time is the ceiling the MSDeformAttn gather can reach on this part.
+__global__ void __launch_bounds__(256)
+l1_gather_probe_kernel(const float4* __restrict__ table, float4* __restrict__ sink, uint32_t rows, int iters) {
+  const uint32_t gid = (blockIdx.x * 256u + threadIdx.x) >> 3;
+  const int j = threadIdx.x & 7;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t h = gid * 2654435761u + 12345u;
+#pragma unroll 8
+  for (int i = 0; i < iters; ++i) {
+    h = h * 1664525u + 1013904223u;
+    const float4 v = __ldg(table + size_t((h >> 8) % rows) * 8 + j);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  if (acc.x == 1.2345e30f) sink[gid] = acc;        // never true: keeps the loads alive
+}
+
 // ---- host-buffer convenience path (end-to-end timing, C callers without a CUDA runtime) ---
 struct DevBuf {
   void* p = nullptr;
@@ -398,6 +429,13 @@ void msda_b200_set_variant(int fwd_variant, int bwd_variant) {
 }
 
 uint64_t msda_b200_launch_count(void) { return g_launches.load(); }
+
+int msda_b200_l1_gather_probe(const float* table, float* sink, int64_t rows, int iters, int ctas, void* stream) {
+  if (!table || !sink || rows <= 0 || iters <= 0 || ctas <= 0) return MSDA_E_DIMS;
+  l1_gather_probe_kernel<<<ctas, 256, 0, cudaStream_t(stream)>>>(reinterpret_cast<const float4*>(table),
+                                                                 reinterpret_cast<float4*>(sink), uint32_t(rows), iters);
+  return int(cudaGetLastError());
+}
 
 int msda_b200_variant_allows_tiles(void) { return g_fwd_variant.load() == 0 ? 1 : 0; }
 
