@@ -116,3 +116,20 @@ def test_add_track_queries_bit_exact_against_reference():
             assert np.array_equal(res[k], gold[k]), k      # indices and masks: bit-exact
         else:
             assert np.array_equal(res[k], gold[k]), k      # gathered rows of identical inputs: also exact
+
+
+def test_msdeformattn_init_constants_match_reference_recipe():
+    """ms_deform_attn.py:33-47: zero offset/attention weights, compass-grid offset bias x (point index + 1),
+    zero attention/value/output biases."""
+    from trackformer_b200.msda_module import MSDeformAttn
+    m = MSDeformAttn(256, 4, 8, 4)
+    grid = torch.tensor([-1, -1, -1, 0, -1, 1, 0, -1, 0, 1, 1, -1, 1, 0, 1, 1], dtype=torch.float32)
+    grid = grid.view(8, 1, 1, 2).repeat(1, 4, 4, 1)
+    for i in range(4):
+        grid[:, :, i, :] *= i + 1
+    assert torch.equal(m.sampling_offsets.bias.detach(), grid.view(-1))
+    assert m.sampling_offsets.bias.requires_grad
+    for t in (m.sampling_offsets.weight, m.attention_weights.weight, m.attention_weights.bias, m.value_proj.bias,
+              m.output_proj.bias):
+        assert not t.detach().any()
+    assert m.value_proj.weight.detach().abs().max() > 0 and m.output_proj.weight.detach().abs().max() > 0

@@ -16,7 +16,6 @@ import torch
 import torch.nn.functional as F
 import torchvision
 from torch import nn
-from torchvision.models._utils import IntermediateLayerGetter
 
 from .position_encoding import build_position_encoding
 from .util import NestedTensor
@@ -51,21 +50,45 @@ def _resize_mask(mask: torch.Tensor, size) -> torch.Tensor:
     return out
 
 
+class _Trunk(nn.ModuleDict):
+    """The convolutional trunk of a torchvision ResNet as an ordered dict of its stages (``conv1 .. layer4``; the
+    classifier head is dropped).  ``forward`` runs the stages in order and collects the outputs listed in ``taps``
+    (stage name -> output key).  Registered under the attribute name ``body`` so that parameter names stay
+    ``backbone.0.body.<stage>...`` like the reference's IntermediateLayerGetter-based trunk (backbone.py:70-78)."""
+
+    def __init__(self, resnet: nn.Module, taps: Dict[str, str]):
+        last = max(i for i, (name, _) in enumerate(resnet.named_children()) if name in taps)
+        super().__init__({name: mod for i, (name, mod) in enumerate(resnet.named_children()) if i <= last})
+        self.taps = dict(taps)
+
+    def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+        collected = {}
+        for name, stage in self.items():
+            x = stage(x)
+            key = self.taps.get(name)
+            if key is not None:
+                collected[key] = x
+        return collected
+
+
 class BackboneBase(nn.Module):
+    #: (strides, channels) of the four residual stages / of the last stage only
+    _PYRAMID = ([4, 8, 16, 32], [256, 512, 1024, 2048])
+
     def __init__(self, backbone: nn.Module, train_backbone: bool, return_interm_layers: bool):
         super().__init__()
-        for name, p in backbone.named_parameters():
-            if not train_backbone or not any(k in name for k in ("layer2", "layer3", "layer4")):
-                p.requires_grad_(False)
+        trainable_stages = ("layer2", "layer3", "layer4") if train_backbone else ()
+        for pname, param in backbone.named_parameters():         # stem and layer1 are always frozen (backbone.py:63-68)
+            if not any(stage in pname for stage in trainable_stages):
+                param.requires_grad_(False)
+        strides, channels = self._PYRAMID
         if return_interm_layers:
-            layers = {"layer1": "0", "layer2": "1", "layer3": "2", "layer4": "3"}
-            self.strides = [4, 8, 16, 32]
-            self.num_channels = [256, 512, 1024, 2048]
+            taps = {f"layer{i + 1}": str(i) for i in range(4)}
+            self.strides, self.num_channels = list(strides), list(channels)
         else:
-            layers = {"layer4": "0"}
-            self.strides = [32]
-            self.num_channels = [2048]
-        self.body = IntermediateLayerGetter(backbone, return_layers=layers)
+            taps = {"layer4": "0"}
+            self.strides, self.num_channels = strides[-1:], channels[-1:]
+        self.body = _Trunk(backbone, taps)
         # NHWC ("channels_last") activations and filters: cuDNN's tensor-core kernels are NHWC-native, so this removes
         # the nchw<->nhwc transposes cuDNN otherwise inserts around every convolution (~1.1 ms per C2 step), and the
         # [N, C, H, W] -> [N, H*W, C] flatten the transformer needs becomes a view.  Values are unchanged.
@@ -81,23 +104,23 @@ class BackboneBase(nn.Module):
             self._filters_nhwc = True
 
     def forward(self, tensor_list: NestedTensor) -> Dict[str, NestedTensor]:
-        x = tensor_list.tensors
-        if self.channels_last and x.is_cuda:
+        frames, pad = tensor_list.tensors, tensor_list.mask
+        assert pad is not None
+        if self.channels_last and frames.is_cuda:
             self.prepare()
-            x = x.contiguous(memory_format=torch.channels_last)
-        feats = self.body(x)
-        mask = tensor_list.mask
-        assert mask is not None
-        return {name: NestedTensor(x, _resize_mask(mask, x.shape[-2:])) for name, x in feats.items()}
+            frames = frames.contiguous(memory_format=torch.channels_last)
+        return {key: NestedTensor(fmap, _resize_mask(pad, fmap.shape[-2:])) for key, fmap in self.body(frames).items()}
 
 
 class Backbone(BackboneBase):
+    """torchvision ResNet trunk with frozen batch-norm; weights are never downloaded here."""
+
     def __init__(self, name: str, train_backbone: bool, return_interm_layers: bool, dilation: bool):
-        net = getattr(torchvision.models, name)(
-            replace_stride_with_dilation=[False, False, dilation], weights=None, norm_layer=FrozenBatchNorm2d)
+        factory = getattr(torchvision.models, name)
+        net = factory(weights=None, norm_layer=FrozenBatchNorm2d, replace_stride_with_dilation=[False, False, dilation])
         super().__init__(net, train_backbone, return_interm_layers)
         if dilation:
-            self.strides[-1] = self.strides[-1] // 2
+            self.strides[-1] //= 2
 
 
 class Joiner(nn.Sequential):

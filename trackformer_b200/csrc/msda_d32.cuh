@@ -219,8 +219,8 @@ __device__ __forceinline__ void red4(float* p, float c, const float4& g) {
   red_add_pack<float, 4>(p, r);
 }
 
-template <int STRIDE_CT>
-__global__ void __launch_bounds__(kD32Threads)
+template <int STRIDE_CT, int MINB = 4>
+__global__ void __launch_bounds__(kD32Threads, MINB)
 msda_bwd_d32_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                     const float* __restrict__ loc, const float* __restrict__ attn,
                     const float* __restrict__ grad_out, float* __restrict__ grad_value,

@@ -334,12 +334,19 @@ static int backward_impl(const T* value, const int64_t* shapes, const T* loc, co
     if (variant != 1 && vec_ok && d.D == 32 && LP <= kMaxLP && aligned16(loc) && aligned16(attn) &&
         aligned16(gloc) && aligned16(gattn) && groups < (int64_t(1) << 31)) {
       const int64_t ctas = (groups + kGroupsPerCta - 1) / kGroupsPerCta;
-      const int iters = variant >= 2 ? variant - 1 : pick_iters(ctas);
+      const int tuning = variant / 10, icode = variant % 10;
+      const int iters = icode >= 2 ? icode - 1 : pick_iters(ctas);
       const unsigned grid = unsigned((ctas + iters - 1) / iters);
       const size_t smem = bwd_d32_smem_bytes(LP);
-      if (d.M == 8)
-        msda_bwd_d32_kernel<256><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, gout, gval, gloc, gattn,
-                                                                  d.S, d.M, d.L, d.Lq, d.P, uint32_t(groups), iters);
+#define MSDA_BWD_D32(B)                                                                                              \
+  msda_bwd_d32_kernel<256, B><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, gout, gval, gloc, gattn, d.S, \
+                                                               d.M, d.L, d.Lq, d.P, uint32_t(groups), iters)
+      if (d.M == 8 && tuning == 1) MSDA_BWD_D32(2);
+      else if (d.M == 8 && tuning == 2) MSDA_BWD_D32(3);
+      else if (d.M == 8 && tuning == 3) MSDA_BWD_D32(5);
+      else if (d.M == 8 && tuning == 4) MSDA_BWD_D32(6);
+      else if (d.M == 8) MSDA_BWD_D32(4);
+#undef MSDA_BWD_D32
       else
         msda_bwd_d32_kernel<0><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, gout, gval, gloc, gattn,
                                                                 d.S, d.M, d.L, d.Lq, d.P, uint32_t(groups), iters);

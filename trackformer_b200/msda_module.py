@@ -50,18 +50,29 @@ class MSDeformAttn(nn.Module):
     def _reset_parameters(self):
         """Reference init (ms_deform_attn.py:33-47): zero offset weights, compass-grid offset bias scaled
         by the point index, zero attention logits, xavier value/output projections."""
-        nn.init.zeros_(self.sampling_offsets.weight)
-        compass = torch.tensor(_COMPASS, dtype=torch.float32)                 # the reference hard-codes 8 heads
-        grid = compass.view(self.n_heads, 1, 1, 2).repeat(1, self.n_levels, self.n_points, 1)
-        grid = grid * torch.arange(1, self.n_points + 1, dtype=torch.float32).view(1, 1, -1, 1)
         with torch.no_grad():
-            self.sampling_offsets.bias = nn.Parameter(grid.reshape(-1))
-        nn.init.zeros_(self.attention_weights.weight)
-        nn.init.zeros_(self.attention_weights.bias)
-        nn.init.xavier_uniform_(self.value_proj.weight)
-        nn.init.zeros_(self.value_proj.bias)
-        nn.init.xavier_uniform_(self.output_proj.weight)
-        nn.init.zeros_(self.output_proj.bias)
+            for lin in (self.sampling_offsets, self.attention_weights):
+                lin.weight.zero_()
+            self.attention_weights.bias.zero_()
+            # head h looks along compass direction h; its k-th point sits k+1 steps out, on every level
+            steps = torch.arange(1, self.n_points + 1, dtype=torch.float32).view(1, 1, self.n_points, 1)
+            rays = torch.tensor(_COMPASS, dtype=torch.float32).view(self.n_heads, 1, 1, 2)   # the reference hard-codes 8 heads
+            self.sampling_offsets.bias = nn.Parameter((rays * steps).expand(-1, self.n_levels, -1, -1).reshape(-1))
+            for lin in (self.value_proj, self.output_proj):
+                nn.init.xavier_uniform_(lin.weight)
+                lin.bias.zero_()
+
+    def _sampling_locations(self, reference_points, offsets, spatial_shapes):
+        """Normalised (x, y) of every sample: reference point + offset.  2-d references: offsets are in pixels of the
+        level, divided by ``spatial_shapes`` as stored -- (H, W), like the reference (ms_deform_attn.py:78-79);
+        4-d references (boxes): offsets are fractions of half the box size, split over the points (:80-82)."""
+        kind = reference_points.shape[-1]
+        if kind == 2:
+            return reference_points[:, :, None, :, None, :] + offsets / spatial_shapes[None, None, None, :, None, :]
+        if kind == 4:
+            centre, size = reference_points[:, :, None, :, None, :2], reference_points[:, :, None, :, None, 2:]
+            return centre + offsets / self.n_points * size * 0.5
+        raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(kind))
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes,
                 input_padding_mask=None, query_attn_mask=None):
@@ -69,8 +80,8 @@ class MSDeformAttn(nn.Module):
         input_flatten [N,S,C]; input_spatial_shapes [L,2]=(H,W) int64; input_padding_mask [N,S] True=pad.
         Returns [N,Lq,C]."""
         n, len_q, _ = query.shape
-        _, len_in, _ = input_flatten.shape
-        m, lv, pt = self.n_heads, self.n_levels, self.n_points
+        len_in = input_flatten.shape[1]
+        heads, levels, points = self.n_heads, self.n_levels, self.n_points
         hw = getattr(input_spatial_shapes, "_hw_list", None)      # host copy attached by the transformer
         if hw is not None:
             assert sum(h * w for h, w in hw) == len_in
@@ -80,32 +91,24 @@ class MSDeformAttn(nn.Module):
         value = fused_linear(input_flatten, self.value_proj.weight, self.value_proj.bias)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], 0.0)
-        value = value.view(n, len_in, m, self.d_model // m)
+        value = value.view(n, len_in, heads, self.d_model // heads)
 
         # one GEMM for [offsets | logits]
-        n_off = m * lv * pt * 2
-        w_cat = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
-        b_cat = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
-        proj = fused_linear(query, w_cat, b_cat)
-        offsets = proj[..., :n_off].reshape(n, len_q, m, lv, pt, 2)
-        attn = F.softmax(proj[..., n_off:].reshape(n, len_q, m, lv * pt), -1).view(n, len_q, m, lv, pt)
+        n_off = heads * levels * points * 2
+        proj = fused_linear(query, torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0),
+                            torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0))
+        offsets = proj[..., :n_off].reshape(n, len_q, heads, levels, points, 2)
+        attn = F.softmax(proj[..., n_off:].reshape(n, len_q, heads, levels * points), -1)
+        attn = attn.view(n, len_q, heads, levels, points)
         if query_attn_mask is not None:
             attn = attn.masked_fill(query_attn_mask[..., None, None, None], 0.0)
-
-        if reference_points.shape[-1] == 2:
-            locations = reference_points[:, :, None, :, None, :] \
-                + offsets / input_spatial_shapes[None, None, None, :, None, :]
-        elif reference_points.shape[-1] == 4:
-            locations = reference_points[:, :, None, :, None, :2] \
-                + offsets / pt * reference_points[:, :, None, :, None, 2:] * 0.5
-        else:
-            raise ValueError(
-                "Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
+        locations = self._sampling_locations(reference_points, offsets, input_spatial_shapes)
 
         if _TILED_ENC and hw is not None and len_q == len_in and value.is_cuda:
             # encoder self-attention: queries are the pixels -> shared-memory tiled forward kernel (opt-in:
             # bit-identical but currently slower than the direct kernel)
-            out = MSDeformAttnEncFunction.apply(value, input_spatial_shapes, locations, attn, self.im2col_step)
+            core = MSDeformAttnEncFunction
         else:
-            out = MSDeformAttnFunction.apply(value, input_spatial_shapes, locations, attn, self.im2col_step)
+            core = MSDeformAttnFunction
+        out = core.apply(value, input_spatial_shapes, locations, attn, self.im2col_step)
         return fused_linear(out, self.output_proj.weight, self.output_proj.bias)
