@@ -51,6 +51,16 @@ int tfb200_relu_dropout_fwd_f32(const float* a, float* h, const int64_t* seed_de
 int tfb200_relu_dropout_bwd_f32(const float* grad_h, const float* h, float* grad_a, int64_t n, float keep_prob,
                                 int training, void* stream);
 
+/* Device-side Hungarian matching (replaces the host scipy.optimize.linear_sum_assignment calls of
+ * src/trackformer/models/matcher.py:104,127).  cost: [K][B][Q][T] fp32 (K decoder layers, B images, Q queries, T = all
+ * ground-truth boxes of the batch, image b owning columns offsets[b] .. offsets[b+1]-1; offsets_dev: int32 [B+1] on the
+ * device).  Every (k, b) problem assigns each of image b's boxes to a distinct query (boxes per image <= max_targets <= Q).
+ * src/tgt: int64 [K][T]; for each problem the pairs are written to columns offsets[b].. in ascending query order:
+ * src = query index, tgt = global box index.  *status_dev (int32, caller-zeroed) becomes 1 (more boxes than queries)
+ * or 2 (infeasible: a box whose costs are all +inf).  Double-precision duals, like scipy.                           */
+int tfb200_lsa_f32(const float* cost, const int* offsets_dev, int64_t* src, int64_t* tgt, int K, int B, int Q, int T,
+                   int max_targets, int* status_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,8 @@ Mask losses belong to the segmentation heads, which are outside the hot path.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -33,6 +35,10 @@ class SetCriterion(nn.Module):
         self.focal_gamma = focal_gamma
         self.tracking = tracking
         self.track_query_false_positive_eos_weight = track_query_false_positive_eos_weight
+        # solve the assignment problems on the GPU (csrc/lsa.cu) when the outputs live there; TFB200_DEVICE_LSA=0
+        # restores the reference's host scipy path
+        self.device_matcher = os.environ.get("TFB200_DEVICE_LSA", "1") != "0"
+        self._index_memo = {}
 
     # ---- index helpers -----------------------------------------------------------------------
     @staticmethod
@@ -152,17 +158,36 @@ class SetCriterion(nn.Module):
             out["aux_outputs"] = layers[:-1]
             return self.forward(out, targets)
 
-        all_indices = self.matcher.match_layers(layers, targets)            # [K][B] (src, tgt) on the host
-        num_boxes = self._num_boxes(targets, logits.device)
         dev = logits.device
         per_layer = sum(sizes)
-        lay = torch.arange(k).repeat_interleave(per_layer)
-        bat = torch.cat([torch.full_like(src, b) for ind in all_indices for b, (src, _) in enumerate(ind)])
-        src = torch.cat([s_ for ind in all_indices for (s_, _) in ind])
-        tgt = torch.cat([t_ + off for ind in all_indices
-                         for (_, t_), off in zip(ind, [sum(sizes[:b]) for b in range(bs)])])
-        idx = torch.stack([lay, bat, src, tgt]).to(dev, non_blocking=True)
-        lay, bat, src, tgt = idx[0], idx[1], idx[2], idx[3]
+        device_match = None
+        if self.device_matcher and hasattr(self.matcher, "match_layers_device"):
+            device_match = self.matcher.match_layers_device(logits.detach(), boxes.detach(), targets)
+        if device_match is not None:
+            # Hungarian matching on the device: no host synchronisation anywhere in the loss
+            src2d, tgt2d, status = device_match
+            torch._assert_async(status[0] == 0)
+            key = (tuple(sizes), k, dev)
+            memo = self._index_memo.get(key)
+            if memo is None:
+                lay = torch.arange(k).repeat_interleave(per_layer)
+                bat = torch.cat([torch.full((n,), b, dtype=torch.int64) for b, n in enumerate(sizes)]).repeat(k)
+                memo = self._index_memo[key] = (lay.to(dev), bat.to(dev),
+                                                torch.as_tensor(sizes, dtype=torch.float, device=dev))
+            lay, bat, n_gt = memo
+            src, tgt = src2d.reshape(-1), tgt2d.reshape(-1)
+            num_boxes = self._num_boxes(targets, dev)
+        else:
+            all_indices = self.matcher.match_layers(layers, targets)        # [K][B] (src, tgt) on the host
+            num_boxes = self._num_boxes(targets, dev)
+            lay = torch.arange(k).repeat_interleave(per_layer)
+            bat = torch.cat([torch.full_like(src, b) for ind in all_indices for b, (src, _) in enumerate(ind)])
+            src = torch.cat([s_ for ind in all_indices for (s_, _) in ind])
+            tgt = torch.cat([t_ + off for ind in all_indices
+                             for (_, t_), off in zip(ind, [sum(sizes[:b]) for b in range(bs)])])
+            idx = torch.stack([lay, bat, src, tgt]).to(dev, non_blocking=True)
+            lay, bat, src, tgt = idx[0], idx[1], idx[2], idx[3]
+            n_gt = torch.as_tensor(sizes, device=dev, dtype=torch.float)
         gt_labels = torch.cat([t["labels"] for t in targets])[tgt]
         gt_boxes = torch.cat([t["boxes"] for t in targets])[tgt]
 
@@ -187,7 +212,6 @@ class SetCriterion(nn.Module):
         loss_giou = (1 - giou).view(k, per_layer).sum(1) / num_boxes
 
         with torch.no_grad():
-            n_gt = torch.as_tensor(sizes, device=dev, dtype=torch.float)
             n_pred = (logits.argmax(-1) != logits.shape[-1] - 1).sum(2).float()                  # [K,B]
             card = (n_pred - n_gt[None]).abs().mean(1)                                           # [K]
             last = slice((k - 1) * per_layer, None)

@@ -249,6 +249,24 @@ at::Tensor relu_dropout_backward(const at::Tensor& grad_h, const at::Tensor& h, 
   return ga;
 }
 
+// cost [K,B,Q,T] fp32, offsets int32 [B+1] (device) -> {src [K,T] int64, tgt [K,T] int64, status int32 [1]}
+std::vector<at::Tensor> lsa(const at::Tensor& cost, const at::Tensor& offsets, int64_t max_targets) {
+  TORCH_CHECK(cost.is_cuda() && cost.scalar_type() == at::kFloat && cost.dim() == 4, "lsa: cost must be a [K,B,Q,T] fp32 CUDA tensor");
+  TORCH_CHECK(offsets.is_cuda() && offsets.scalar_type() == at::kInt && offsets.numel() == cost.size(1) + 1,
+              "lsa: offsets must be an int32 CUDA tensor of B+1 entries");
+  const at::Tensor c = cost.contiguous();
+  const c10::cuda::CUDAGuard guard(cost.device());
+  const int64_t K = c.size(0), B = c.size(1), Q = c.size(2), T = c.size(3);
+  auto iopt = c.options().dtype(at::kLong);
+  at::Tensor src = at::zeros({K, T}, iopt), tgt = at::zeros({K, T}, iopt);
+  at::Tensor status = at::zeros({1}, c.options().dtype(at::kInt));
+  const int rc = tfb200_lsa_f32(c.data_ptr<float>(), offsets.data_ptr<int>(), src.data_ptr<int64_t>(), tgt.data_ptr<int64_t>(),
+                                int(K), int(B), int(Q), int(T), int(max_targets), status.data_ptr<int>(),
+                                c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "lsa failed (code ", rc, ")");
+  return {src, tgt, status};
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200 (sm_100a) multi-scale deformable attention; drop-in for the reference extension";
   m.def("ms_deform_attn_forward", &ms_deform_attn_forward, "ms_deform_attn_forward");
@@ -261,6 +279,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("add_dropout_layernorm_forward", &add_dropout_layernorm_forward);
   m.def("add_dropout_layernorm_backward", &add_dropout_layernorm_backward);
   m.def("colsum", &colsum);
+  m.def("lsa", &lsa);
   m.def("relu_dropout_forward", &relu_dropout_forward);
   m.def("relu_dropout_backward", &relu_dropout_backward);
 }

@@ -27,6 +27,7 @@ class HungarianMatcher(nn.Module):
         self.focal_loss = focal_loss
         self.focal_alpha = focal_alpha
         self.focal_gamma = focal_gamma
+        self._offsets_memo = {}
 
     def _cost(self, logits, boxes, tgt_ids, tgt_boxes):
         """[Q', C] logits, [Q', 4] boxes against all T ground-truth boxes of the batch -> [Q', T] cost."""
@@ -62,6 +63,31 @@ class HungarianMatcher(nn.Module):
             result.append([(torch.as_tensor(r, dtype=torch.int64), torch.as_tensor(c, dtype=torch.int64))
                            for r, c in picks])
         return result
+
+    @torch.no_grad()
+    def match_layers_device(self, logits, boxes, targets):
+        """All K layers' matchings ON THE DEVICE (csrc/lsa.cu): no device->host transfer, CUDA-graph capturable.
+        ``logits [K,B,Q,C]``, ``boxes [K,B,Q,4]`` -> ``(src [K,T], tgt [K,T], status)`` with T = total number of
+        boxes; for image b the columns ``off[b]..off[b+1]-1`` hold its (query, box) pairs in ascending query order --
+        the pairs scipy returns (the optimum is unique unless costs tie exactly).  Returns ``None`` when the device
+        solver does not apply (track-query forcing, more boxes than queries, CPU tensors)."""
+        from . import ext
+        k, bs, nq, _ = logits.shape
+        sizes = [len(t["boxes"]) for t in targets]
+        if (not logits.is_cuda or any("track_query_match_ids" in t for t in targets) or max(sizes) > nq
+                or sum(sizes) == 0):
+            return None
+        tgt_ids = torch.cat([t["labels"] for t in targets])
+        tgt_boxes = torch.cat([t["boxes"] for t in targets])
+        cost = self._cost(logits.flatten(0, 2), boxes.flatten(0, 2), tgt_ids, tgt_boxes).view(k, bs, nq, -1)
+        key = (tuple(sizes), logits.device)
+        off = self._offsets_memo.get(key)
+        if off is None:
+            acc = [0]
+            for n in sizes:
+                acc.append(acc[-1] + n)
+            off = self._offsets_memo[key] = torch.tensor(acc, dtype=torch.int32, device=logits.device)
+        return ext.load().lsa(cost.float(), off, max(sizes))
 
     @torch.no_grad()
     def forward(self, outputs, targets):
