@@ -174,6 +174,8 @@ def main():
     ap.add_argument("--no-tf32", action="store_true", help="strict fp32 GEMMs/convs (default: TF32 tensor cores)")
     ap.add_argument("--no-optimizer", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="eager step instead of CUDA-graph replay")
+    ap.add_argument("--two-graphs", action="store_true",
+                    help="forward graph + eager loss + backward graph instead of the single full-step graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
     args = ap.parse_args()
@@ -232,7 +234,7 @@ def main():
     opt_factory = None if args.no_optimizer else (
         lambda ps: torch.optim.AdamW(ps, lr=2e-4, weight_decay=1e-4, fused=True))
     step = TrainStep(model, criterion, opt_factory, max_norm=0.1, use_graphs=not args.no_graphs,
-                     example_frames=dev_frames)
+                     example_frames=dev_frames, example_targets=None if args.two_graphs else targets)
 
     def barrier():
         if world > 1:
@@ -360,8 +362,10 @@ def main():
                    "msda_math": "fp32 (hand-written sm_100a kernels)", "dropout": 0.1,
                    "optimizer": "none" if args.no_optimizer else "AdamW(fused) + clip_grad_norm 0.1",
                    "execution": "eager" if args.no_graphs else
-                   "model forward + backward replayed from CUDA graphs; Hungarian matching (scipy, host) and the loss "
-                   "run between the two graphs; flat-buffer gradient all-reduce (NCCL) after the backward graph",
+                   ("forward graph + loss (device Hungarian matching, no host sync) + backward graph" if args.two_graphs else
+                    "ONE CUDA graph per step: forward + matching cost + device Hungarian matching (csrc/lsa.cu) + loss + "
+                    "backward incl. gradient accumulation") + "; flat-buffer gradient all-reduce (NCCL), clip and fused "
+                   "AdamW follow the replay",
                    "gpu_launches_note": f"{launches_per_step} own kernel launches per step "
                                         "(12 MSDeformAttn forward + 12 backward), replayed from the graphs",
                    "weights": "random init", "gt_boxes_per_frame": N_GT,

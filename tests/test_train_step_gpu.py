@@ -42,6 +42,30 @@ def test_graph_replay_equals_eager(cuda_device):
         torch.testing.assert_close(graphed.flat_grad, eager.flat_grad, rtol=1e-3, atol=2e-4 * scale)
 
 
+def test_full_step_graph_equals_eager(cuda_device):
+    """forward + device matching + loss + backward captured as ONE graph; ground truth of the captured box count is
+    fed through static buffers, other counts fall back to the two-graph path."""
+    from trackformer_b200.train_step import TrainStep
+    dev = cuda_device
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    model, criterion = small_model(dev)
+    model_e = copy.deepcopy(model)
+    g = torch.Generator().manual_seed(4)
+    frames = [torch.randn(1, 3, 192, 256, generator=g).to(dev) for _ in range(3)]
+    full = TrainStep(model, criterion, None, use_graphs=True, example_frames=frames[0],
+                     example_targets=targets_for(dev, 0, 5))
+    assert full.g_full is not None
+    eager = TrainStep(model_e, criterion, None, use_graphs=False)
+    for i, (f, n) in enumerate(zip(frames, (5, 5, 8))):          # third step: different box count -> fallback path
+        tg = targets_for(dev, 20 + i, n)
+        loss_g = full(f, tg).clone()
+        loss_e = eager(f, tg)
+        torch.testing.assert_close(loss_g, loss_e, rtol=1e-4, atol=1e-4)
+        scale = float(eager.flat_grad.abs().max())
+        torch.testing.assert_close(full.flat_grad, eager.flat_grad, rtol=1e-3, atol=2e-4 * scale)
+
+
 def test_optimizer_step_updates_weights_and_clips(cuda_device):
     from trackformer_b200.train_step import TrainStep
     dev = cuda_device

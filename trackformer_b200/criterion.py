@@ -142,7 +142,7 @@ class SetCriterion(nn.Module):
             return torch.clamp(t / get_world_size(), min=1).item()
         return float(max(n_boxes, 1))
 
-    def forward_stacked(self, logits, boxes, targets):
+    def forward_stacked(self, logits, boxes, targets, num_boxes=None):
         """Same losses as ``forward`` for a detector whose K decoder layers arrive stacked --
         ``logits [K,B,Q,C]``, ``boxes [K,B,Q,4]``, last layer = final prediction -- computed in ONE pass over
         all layers instead of K passes (the reference loops, detr.py:404-424): one Hungarian transfer, one focal
@@ -176,10 +176,12 @@ class SetCriterion(nn.Module):
                                                 torch.as_tensor(sizes, dtype=torch.float, device=dev))
             lay, bat, n_gt = memo
             src, tgt = src2d.reshape(-1), tgt2d.reshape(-1)
-            num_boxes = self._num_boxes(targets, dev)
+            if num_boxes is None:               # callers replaying a captured step pass the (static) normaliser in
+                num_boxes = self._num_boxes(targets, dev)
         else:
             all_indices = self.matcher.match_layers(layers, targets)        # [K][B] (src, tgt) on the host
-            num_boxes = self._num_boxes(targets, dev)
+            if num_boxes is None:
+                num_boxes = self._num_boxes(targets, dev)
             lay = torch.arange(k).repeat_interleave(per_layer)
             bat = torch.cat([torch.full_like(src, b) for ind in all_indices for b, (src, _) in enumerate(ind)])
             src = torch.cat([s_ for ind in all_indices for (s_, _) in ind])

@@ -47,7 +47,8 @@ class TrainStep:
     """``loss = step(frames, targets)`` -- forward, criterion, backward, [all-reduce], clip, optimizer."""
 
     def __init__(self, model, criterion, optimizer_factory=None, max_norm: float = 0.1,
-                 use_graphs: bool = True, example_frames: Optional[torch.Tensor] = None):
+                 use_graphs: bool = True, example_frames: Optional[torch.Tensor] = None,
+                 example_targets: Optional[list] = None):
         self.model = model
         self.criterion = criterion
         self.max_norm = max_norm
@@ -57,7 +58,10 @@ class TrainStep:
             prepare()                                   # final parameter memory formats before gradient views exist
         self.params: List[nn.Parameter] = [p for p in model.parameters() if p.requires_grad]
         self.core = _DetectorCore(model)
-        self.g_fwd = self.g_bwd = None
+        # with several ranks the loss normaliser is the world-averaged box count: the full-step graph bakes it in, which
+        # is only valid while every rank keeps its box counts (the benchmark does); variable data uses the two-graph path
+        self._static_world_boxes = True
+        self.g_fwd = self.g_bwd = self.g_full = None
 
         # flat gradient buffer: param.grad are views -> one zero-fill, one all-reduce, one norm
         total = sum(p.numel() for p in self.params)
@@ -76,6 +80,8 @@ class TrainStep:
         if use_graphs:
             assert example_frames is not None and example_frames.is_cuda
             self._capture(example_frames)
+            if example_targets is not None and getattr(criterion, "device_matcher", False):
+                self._capture_full(example_targets)
 
     # ------------------------------------------------------------------------------------------
     def _capture(self, example: torch.Tensor) -> None:
@@ -91,7 +97,7 @@ class TrainStep:
                 torch.autograd.backward((lg, bx), (torch.zeros_like(lg), torch.zeros_like(bx)))
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        pool = torch.cuda.graph_pool_handle()
+        pool = self._pool = torch.cuda.graph_pool_handle()
         self.g_fwd = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.g_fwd, pool=pool):
             self.s_logits, self.s_boxes = self.core(self.static_frames)
@@ -103,13 +109,51 @@ class TrainStep:
             torch.autograd.backward((self.s_logits, self.s_boxes), (self.s_glogits, self.s_gboxes))
         self.flat_grad.zero_()
 
-    def _loss(self, logits, boxes, targets):
-        loss_dict = self.criterion.forward_stacked(logits, boxes, targets)
+    def _capture_full(self, example_targets: list) -> None:
+        """ONE graph for forward + matching cost + device Hungarian matching + loss + backward, usable whenever the
+        ground truth has the captured per-image box counts (boxes / labels are copied into static buffers).  Other
+        box counts take the two-graph path with the loss in between."""
+        self.full_sizes = tuple(len(t["labels"]) for t in example_targets)
+        if min(self.full_sizes) == 0:
+            return
+        self.s_targets = [{"boxes": t["boxes"].clone(), "labels": t["labels"].clone()} for t in example_targets]
+        dev = self.static_frames.device
+        self.s_num_boxes = self.criterion._num_boxes(self.s_targets, dev)      # static normaliser (may sync once)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                                            # memos, lazy inits
+            for _ in range(2):
+                lg, bx = self.core(self.static_frames)
+                self._loss(lg, bx, self.s_targets, self.s_num_boxes).backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=self._pool):
+            self.flat_grad.zero_()
+            lg, bx = self.core(self.static_frames)
+            loss = self._loss(lg, bx, self.s_targets, self.s_num_boxes)
+            loss.backward()
+            self.s_loss = loss.detach()
+        self.g_full = g
+        self.flat_grad.zero_()
+
+    def _loss(self, logits, boxes, targets, num_boxes=None):
+        loss_dict = self.criterion.forward_stacked(logits, boxes, targets, num_boxes)
         wd = self.criterion.weight_dict
         return sum(loss_dict[k] * wd[k] for k in loss_dict if k in wd)
 
     def __call__(self, frames: torch.Tensor, targets: list) -> torch.Tensor:
-        if self.g_fwd is not None:
+        if self.g_full is not None and tuple(len(t["labels"]) for t in targets) == self.full_sizes \
+                and (self.world == 1 or self._static_world_boxes):
+            if frames is not self.static_frames:
+                self.static_frames.copy_(frames, non_blocking=True)     # device or pinned-host source
+            for st, t in zip(self.s_targets, targets):
+                if t["boxes"] is not st["boxes"]:
+                    st["boxes"].copy_(t["boxes"], non_blocking=True)
+                    st["labels"].copy_(t["labels"], non_blocking=True)
+            self.g_full.replay()
+            loss = self.s_loss
+        elif self.g_fwd is not None:
             if frames is not self.static_frames:
                 self.static_frames.copy_(frames, non_blocking=True)     # device or pinned-host source
             self.g_fwd.replay()
