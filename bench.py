@@ -196,8 +196,11 @@ def main():
         line = {"impl": "reference", "metric": "frames/sec Deformable-DETR R50 800x1333 fwd+bwd", "value": fps,
                 "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": {"workload": workload, "device": "cpu",
-                                                 "bounded_sample": f"{steps} timed step(s) of {bpg} frame(s) after {warm} warm-up"},
+                "data": "synthetic",
+                "config": {"workload": workload, "global_batch": bpg * args.gpus, "parallelism": f"dp{args.gpus}",
+                           "device": "host CPU cores (reference pure-PyTorch ms_deform_attn path)", "dropout": 0.1,
+                           "optimizer": "AdamW + clip_grad_norm 0.1", "weights": "random init", "gt_boxes_per_frame": N_GT,
+                           "bounded_sample": f"{steps} timed step(s) of {bpg} frame(s) after {warm} warm-up on rank 0"},
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                  "sample": f"{steps} full train step(s), pure-PyTorch grid_sample MSDeformAttn (oracle/torch_ref.py)"},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -1,6 +1,5 @@
 """GPU-vs-GPU parity against the reference's OWN CUDA kernels (compiled for sm_100a from /root/reference by
 oracle/Makefile `ref` in the build container; the shared object travels to the GPU box).  Skipped when it was not built."""
-import numpy as np
 import pytest
 import torch
 

@@ -2,7 +2,6 @@
 """Where does a training step spend its time?  Phase timers (host wall-clock with device syncs) and a
 torch.profiler kernel table for the CUDA-graph TrainStep.  Diagnostic tool, not part of the benchmark."""
 import argparse
-import json
 import os
 import sys
 import time

@@ -22,7 +22,7 @@ flat all-reduce keeps the backward capturable and costs one launch.)
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist
