@@ -51,6 +51,17 @@ int tfb200_relu_dropout_fwd_f32(const float* a, float* h, const int64_t* seed_de
 int tfb200_relu_dropout_bwd_f32(const float* grad_h, const float* h, float* grad_a, int64_t n, float keep_prob,
                                 int training, void* stream);
 
+/* proj [rows][3*M*L*P] = per query [offsets (M,L,P,2) | attention logits (M,L*P)]  ->  sampling locations
+ * loc [rows][M][L][P][2] and softmax attention weights attn [rows][M][L][P] in one pass (ms_deform_attn.py:69-82).
+ * ref: [rows][L][ref_dim] reference points (ref_dim 2) or boxes (4); shapes_f32: [L][2] level sizes AS STORED (H, W)
+ * in fp32 (only read for ref_dim == 2).  L*P in {4, 8, 16, 32}, (M*L*P) % 32 == 0.  backward: grad_proj from grad_loc,
+ * grad_attn and the saved attn (no gradient for ref: callers use it only when ref does not require one).            */
+int tfb200_sampling_prep_fwd_f32(const float* proj, const float* ref, const float* shapes_f32, float* loc, float* attn,
+                                 int64_t rows, int M, int L, int P, int ref_dim, void* stream);
+int tfb200_sampling_prep_bwd_f32(const float* grad_loc, const float* grad_attn, const float* attn, const float* ref,
+                                 const float* shapes_f32, float* grad_proj, int64_t rows, int M, int L, int P, int ref_dim,
+                                 void* stream);
+
 /* Device-side Hungarian matching (replaces the host scipy.optimize.linear_sum_assignment calls of
  * src/trackformer/models/matcher.py:104,127).  cost: [K][B][Q][T] fp32 (K decoder layers, B images, Q queries, T = all
  * ground-truth boxes of the batch, image b owning columns offsets[b] .. offsets[b+1]-1; offsets_dev: int32 [B+1] on the

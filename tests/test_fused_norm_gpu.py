@@ -124,3 +124,30 @@ def test_relu_dropout(dev):
     assert float((col - 0.9).abs().max()) < 0.02
     g1, = torch.autograd.grad(h1, a, torch.ones_like(h1))
     torch.testing.assert_close(g1, kept.float() / 0.9)
+
+
+@pytest.mark.parametrize("ref_dim,L,P,Lq", [(2, 4, 4, 22223), (4, 4, 4, 300), (2, 8, 4, 777), (4, 2, 4, 64), (2, 1, 4, 33)])
+def test_sampling_prep_matches_torch_chain(dev, ref_dim, L, P, Lq):
+    """One fused pass == the reference's split / softmax / normalise / add chain (ms_deform_attn.py:69-82)."""
+    from trackformer_b200.msda_module import _SamplingPrep
+    M, N = 8, 2 if Lq < 1000 else 1
+    g = torch.Generator().manual_seed(L * 10 + P + ref_dim)
+    proj = torch.randn(N, Lq, 3 * M * L * P, generator=g).to(dev).requires_grad_(True)
+    ref = torch.rand(N, Lq, L, ref_dim, generator=g).to(dev)
+    shapes = torch.tensor([(100 // (l + 1) + 3, 167 // (l + 1) + 2) for l in range(L)], dtype=torch.long, device=dev)
+    loc, attn = _SamplingPrep.apply(proj, ref, shapes.float(), M, L, P)
+    # reference chain
+    p2 = proj.detach().clone().requires_grad_(True)
+    n_off = M * L * P * 2
+    off = p2[..., :n_off].reshape(N, Lq, M, L, P, 2)
+    a_ref = torch.softmax(p2[..., n_off:].reshape(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+    if ref_dim == 2:
+        l_ref = ref[:, :, None, :, None, :] + off / shapes[None, None, None, :, None, :]
+    else:
+        l_ref = ref[:, :, None, :, None, :2] + off / P * ref[:, :, None, :, None, 2:] * 0.5
+    torch.testing.assert_close(loc, l_ref, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(attn, a_ref, rtol=1e-5, atol=1e-7)
+    gl, ga = torch.randn_like(loc), torch.randn_like(attn)
+    (g1,) = torch.autograd.grad([loc, attn], [proj], [gl, ga])
+    (g2,) = torch.autograd.grad([l_ref, a_ref], [p2], [gl, ga])
+    torch.testing.assert_close(g1, g2, rtol=1e-4, atol=1e-6)

@@ -375,3 +375,154 @@ int tfb200_relu_dropout_bwd_f32(const float* grad_h, const float* h, float* grad
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Sampling prep: proj = [offsets (M*L*P*2) | logits (M*L*P)] per query  ->  sampling locations + attention weights.
+// Fuses what the reference's MSDeformAttn.forward does with five PyTorch ops per call (ops/modules/ms_deform_attn.py:
+// 69-82): split + view of the two projections, softmax over the L*P logits of each head, offset normalisation and the
+// reference-point add.  One thread per sample; the LP (power of two <= 32) samples of one (query, head) sit in
+// consecutive lanes, so the softmax is a segmented warp-shuffle reduction and every stream is read/written coalesced.
+//   2-d reference points: loc = ref[l] + off / (shape_l[0], shape_l[1])      (the reference divides (x, y) by (H, W))
+//   4-d reference boxes : loc = ref_xy[l] + off / P * ref_wh[l] * 0.5
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+template <int LP>
+__device__ __forceinline__ float seg_max(float v) {
+#pragma unroll
+  for (int o = LP / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+template <int LP>
+__device__ __forceinline__ float seg_sum(float v) {
+#pragma unroll
+  for (int o = LP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// proj: [rows][3*M*LP] (row = (n, q)); ref: [rows][L][RD]; shapes: [L][2] float; loc: [rows][M][LP][2]; attn: [rows][M][LP]
+template <int LP, int RD>
+__global__ void __launch_bounds__(256)
+sampling_prep_fwd_kernel(const float* __restrict__ proj, const float* __restrict__ ref, const float* __restrict__ shapes,
+                         float* __restrict__ loc, float* __restrict__ attn, int64_t total, int M, int P) {
+  const int64_t stride_t = int64_t(gridDim.x) * 256;
+  const int mlp = M * LP;
+  for (int64_t t0 = int64_t(blockIdx.x) * 256; t0 < total; t0 += stride_t) {   // whole warps stay together (total % 32 == 0)
+    const int64_t t = t0 + threadIdx.x;
+    const bool ok = t < total;
+    const int64_t tt = ok ? t : total - 1;
+    const int64_t row = tt / mlp;
+    const int rem = int(tt - row * mlp);          // m * LP + s
+    const int s = rem % LP, l = s / P;
+    const float* prow = proj + row * 3 * mlp;
+    const float2 off = __ldg(reinterpret_cast<const float2*>(prow) + rem);
+    const float logit = __ldg(prow + 2 * mlp + rem);
+    const float mx = seg_max<LP>(logit);
+    const float e = expf(logit - mx);
+    const float a = e / seg_sum<LP>(e);
+    float2 o;
+    if (RD == 2) {
+      const float2 r = __ldg(reinterpret_cast<const float2*>(ref) + row * (LP / P) + l);
+      o.x = r.x + off.x / __ldg(shapes + 2 * l);
+      o.y = r.y + off.y / __ldg(shapes + 2 * l + 1);
+    } else {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(ref) + row * (LP / P) + l);
+      o.x = r.x + off.x / float(P) * r.z * 0.5f;
+      o.y = r.y + off.y / float(P) * r.w * 0.5f;
+    }
+    if (ok) {
+      reinterpret_cast<float2*>(loc)[t] = o;
+      attn[t] = a;
+    }
+  }
+}
+
+// grad_proj offsets part = grad_loc * d(loc)/d(off); logits part = attn * (ga - sum_s attn*ga)
+template <int LP, int RD>
+__global__ void __launch_bounds__(256)
+sampling_prep_bwd_kernel(const float* __restrict__ grad_loc, const float* __restrict__ grad_attn,
+                         const float* __restrict__ attn, const float* __restrict__ ref, const float* __restrict__ shapes,
+                         float* __restrict__ grad_proj, int64_t total, int M, int P) {
+  const int64_t stride_t = int64_t(gridDim.x) * 256;
+  const int mlp = M * LP;
+  for (int64_t t0 = int64_t(blockIdx.x) * 256; t0 < total; t0 += stride_t) {
+    const int64_t t = t0 + threadIdx.x;
+    const bool ok = t < total;
+    const int64_t tt = ok ? t : total - 1;
+    const int64_t row = tt / mlp;
+    const int rem = int(tt - row * mlp);
+    const int s = rem % LP, l = s / P;
+    const float2 gl = __ldg(reinterpret_cast<const float2*>(grad_loc) + tt);
+    const float ga = __ldg(grad_attn + tt), a = __ldg(attn + tt);
+    const float dot = seg_sum<LP>(a * ga);
+    float2 go;
+    if (RD == 2) {
+      go.x = gl.x / __ldg(shapes + 2 * l);
+      go.y = gl.y / __ldg(shapes + 2 * l + 1);
+    } else {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(ref) + row * (LP / P) + l);
+      go.x = gl.x / float(P) * r.z * 0.5f;
+      go.y = gl.y / float(P) * r.w * 0.5f;
+    }
+    if (ok) {
+      float* grow = grad_proj + row * 3 * mlp;
+      reinterpret_cast<float2*>(grow)[rem] = go;
+      grow[2 * mlp + rem] = a * (ga - dot);
+    }
+  }
+}
+
+int prep_grid(int64_t total) {
+  const int64_t need = (total + 255) / 256;
+  return int(need < 148 * 16 ? need : 148 * 16);
+}
+
+}  // namespace
+
+extern "C" {
+
+int tfb200_sampling_prep_fwd_f32(const float* proj, const float* ref, const float* shapes_f32, float* loc, float* attn,
+                                 int64_t rows, int M, int L, int P, int ref_dim, void* stream) {
+  if (!proj || !ref || !loc || !attn || (ref_dim == 2 && !shapes_f32)) return TFB200_E_NULLPTR;
+  const int LP = L * P;
+  if (rows < 0 || M <= 0 || (ref_dim != 2 && ref_dim != 4) || (LP != 4 && LP != 8 && LP != 16 && LP != 32) ||
+      (int64_t(M) * LP) % 32 != 0)
+    return TFB200_E_SHAPE;
+  const int64_t total = rows * M * LP;
+  if (total == 0) return 0;
+  cudaStream_t st = cudaStream_t(stream);
+#define TFB200_PREP(LP_, RD_) \
+  sampling_prep_fwd_kernel<LP_, RD_><<<prep_grid(total), 256, 0, st>>>(proj, ref, shapes_f32, loc, attn, total, M, P)
+  if (ref_dim == 2) {
+    if (LP == 4) TFB200_PREP(4, 2); else if (LP == 8) TFB200_PREP(8, 2); else if (LP == 16) TFB200_PREP(16, 2); else TFB200_PREP(32, 2);
+  } else {
+    if (LP == 4) TFB200_PREP(4, 4); else if (LP == 8) TFB200_PREP(8, 4); else if (LP == 16) TFB200_PREP(16, 4); else TFB200_PREP(32, 4);
+  }
+#undef TFB200_PREP
+  return int(cudaGetLastError());
+}
+
+int tfb200_sampling_prep_bwd_f32(const float* grad_loc, const float* grad_attn, const float* attn, const float* ref,
+                                 const float* shapes_f32, float* grad_proj, int64_t rows, int M, int L, int P, int ref_dim,
+                                 void* stream) {
+  if (!grad_loc || !grad_attn || !attn || !ref || !grad_proj || (ref_dim == 2 && !shapes_f32)) return TFB200_E_NULLPTR;
+  const int LP = L * P;
+  if (rows < 0 || M <= 0 || (ref_dim != 2 && ref_dim != 4) || (LP != 4 && LP != 8 && LP != 16 && LP != 32) ||
+      (int64_t(M) * LP) % 32 != 0)
+    return TFB200_E_SHAPE;
+  const int64_t total = rows * M * LP;
+  if (total == 0) return 0;
+  cudaStream_t st = cudaStream_t(stream);
+#define TFB200_PREPB(LP_, RD_) \
+  sampling_prep_bwd_kernel<LP_, RD_><<<prep_grid(total), 256, 0, st>>>(grad_loc, grad_attn, attn, ref, shapes_f32, \
+                                                                       grad_proj, total, M, P)
+  if (ref_dim == 2) {
+    if (LP == 4) TFB200_PREPB(4, 2); else if (LP == 8) TFB200_PREPB(8, 2); else if (LP == 16) TFB200_PREPB(16, 2); else TFB200_PREPB(32, 2);
+  } else {
+    if (LP == 4) TFB200_PREPB(4, 4); else if (LP == 8) TFB200_PREPB(8, 4); else if (LP == 16) TFB200_PREPB(16, 4); else TFB200_PREPB(32, 4);
+  }
+#undef TFB200_PREPB
+  return int(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -249,6 +249,35 @@ at::Tensor relu_dropout_backward(const at::Tensor& grad_h, const at::Tensor& h, 
   return ga;
 }
 
+// proj [N,Lq,3*M*L*P], ref [N,Lq,L,2|4], shapes_f32 [L,2] -> {loc [N,Lq,M,L,P,2], attn [N,Lq,M,L,P]}
+std::vector<at::Tensor> sampling_prep_forward(const at::Tensor& proj, const at::Tensor& ref, const at::Tensor& shapes_f32,
+                                              int64_t M, int64_t L, int64_t P) {
+  TORCH_CHECK(proj.is_cuda() && proj.scalar_type() == at::kFloat && proj.dim() == 3, "sampling_prep: proj must be [N,Lq,3*M*L*P] fp32 CUDA");
+  const at::Tensor p = proj.contiguous(), r = ref.contiguous(), sh = shapes_f32.contiguous();
+  const int64_t N = p.size(0), Lq = p.size(1);
+  TORCH_CHECK(p.size(2) == 3 * M * L * P && r.size(0) == N && r.size(1) == Lq && r.size(2) == L, "sampling_prep: shape mismatch");
+  const c10::cuda::CUDAGuard guard(proj.device());
+  at::Tensor loc = at::empty({N, Lq, M, L, P, 2}, p.options()), attn = at::empty({N, Lq, M, L, P}, p.options());
+  const int rc = tfb200_sampling_prep_fwd_f32(p.data_ptr<float>(), r.data_ptr<float>(), sh.data_ptr<float>(),
+                                              loc.data_ptr<float>(), attn.data_ptr<float>(), N * Lq, int(M), int(L), int(P),
+                                              int(r.size(3)), c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "sampling_prep_forward failed (code ", rc, ")");
+  return {loc, attn};
+}
+
+at::Tensor sampling_prep_backward(const at::Tensor& grad_loc, const at::Tensor& grad_attn, const at::Tensor& attn,
+                                  const at::Tensor& ref, const at::Tensor& shapes_f32, int64_t M, int64_t L, int64_t P) {
+  const at::Tensor gl = grad_loc.contiguous(), ga = grad_attn.contiguous(), r = ref.contiguous(), sh = shapes_f32.contiguous();
+  const int64_t N = attn.size(0), Lq = attn.size(1);
+  const c10::cuda::CUDAGuard guard(attn.device());
+  at::Tensor gp = at::empty({N, Lq, 3 * M * L * P}, attn.options());
+  const int rc = tfb200_sampling_prep_bwd_f32(gl.data_ptr<float>(), ga.data_ptr<float>(), attn.data_ptr<float>(),
+                                              r.data_ptr<float>(), sh.data_ptr<float>(), gp.data_ptr<float>(), N * Lq, int(M),
+                                              int(L), int(P), int(r.size(3)), c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "sampling_prep_backward failed (code ", rc, ")");
+  return gp;
+}
+
 // cost [K,B,Q,T] fp32, offsets int32 [B+1] (device) -> {src [K,T] int64, tgt [K,T] int64, status int32 [1]}
 std::vector<at::Tensor> lsa(const at::Tensor& cost, const at::Tensor& offsets, int64_t max_targets) {
   TORCH_CHECK(cost.is_cuda() && cost.scalar_type() == at::kFloat && cost.dim() == 4, "lsa: cost must be a [K,B,Q,T] fp32 CUDA tensor");
@@ -280,6 +309,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("add_dropout_layernorm_backward", &add_dropout_layernorm_backward);
   m.def("colsum", &colsum);
   m.def("lsa", &lsa);
+  m.def("sampling_prep_forward", &sampling_prep_forward);
+  m.def("sampling_prep_backward", &sampling_prep_backward);
   m.def("relu_dropout_forward", &relu_dropout_forward);
   m.def("relu_dropout_backward", &relu_dropout_backward);
 }

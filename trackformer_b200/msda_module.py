@@ -29,6 +29,27 @@ _TILED_ENC = os.environ.get("TFB200_TILED_ENC", "0") == "1"
 _COMPASS = ((-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 1), (1, -1), (1, 0), (1, 1))
 
 
+class _SamplingPrep(torch.autograd.Function):
+    """[offsets | logits] projection -> (sampling locations, softmax attention weights) in one fused kernel
+    (csrc/fused_norm.cu).  Used when the reference points carry no gradient (encoder; decoder layers after the first)."""
+
+    @staticmethod
+    def forward(ctx, proj, ref, shapes_f32, m, lv, pt):
+        from . import ext
+        loc, attn = ext.load().sampling_prep_forward(proj, ref, shapes_f32, m, lv, pt)
+        ctx.save_for_backward(attn, ref, shapes_f32)
+        ctx.dims = (m, lv, pt)
+        return loc, attn
+
+    @staticmethod
+    def backward(ctx, grad_loc, grad_attn):
+        from . import ext
+        attn, ref, shapes_f32 = ctx.saved_tensors
+        m, lv, pt = ctx.dims
+        gp = ext.load().sampling_prep_backward(grad_loc, grad_attn, attn, ref, shapes_f32, m, lv, pt)
+        return gp, None, None, None, None, None
+
+
 class MSDeformAttn(nn.Module):
     def __init__(self, d_model: int = 256, n_levels: int = 4, n_heads: int = 8, n_points: int = 4,
                  im2col_step: int = 64):
@@ -62,13 +83,28 @@ class MSDeformAttn(nn.Module):
                 nn.init.xavier_uniform_(lin.weight)
                 lin.bias.zero_()
 
+    @staticmethod
+    def _float_shapes(spatial_shapes, like):
+        """``spatial_shapes`` as floats, memoised on the (cached) shapes tensor.  Dividing by it gives the same quotient as
+        dividing by the int64 tensor (type promotion converts that to float32 first) but keeps TensorIterator on its
+        vectorised same-dtype path (35 -> ~8 us per C2 encoder call)."""
+        f = getattr(spatial_shapes, "_as_float", None)
+        if f is None or f.dtype != like.dtype:
+            f = spatial_shapes.to(like.dtype)
+            try:
+                spatial_shapes._as_float = f
+            except AttributeError:
+                pass
+        return f
+
     def _sampling_locations(self, reference_points, offsets, spatial_shapes):
         """Normalised (x, y) of every sample: reference point + offset.  2-d references: offsets are in pixels of the
         level, divided by ``spatial_shapes`` as stored -- (H, W), like the reference (ms_deform_attn.py:78-79);
         4-d references (boxes): offsets are fractions of half the box size, split over the points (:80-82)."""
         kind = reference_points.shape[-1]
         if kind == 2:
-            return reference_points[:, :, None, :, None, :] + offsets / spatial_shapes[None, None, None, :, None, :]
+            divisor = self._float_shapes(spatial_shapes, offsets)
+            return reference_points[:, :, None, :, None, :] + offsets / divisor[None, None, None, :, None, :]
         if kind == 4:
             centre, size = reference_points[:, :, None, :, None, :2], reference_points[:, :, None, :, None, 2:]
             return centre + offsets / self.n_points * size * 0.5
@@ -97,12 +133,20 @@ class MSDeformAttn(nn.Module):
         n_off = heads * levels * points * 2
         proj = fused_linear(query, torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0),
                             torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0))
-        offsets = proj[..., :n_off].reshape(n, len_q, heads, levels, points, 2)
-        attn = F.softmax(proj[..., n_off:].reshape(n, len_q, heads, levels * points), -1)
-        attn = attn.view(n, len_q, heads, levels, points)
-        if query_attn_mask is not None:
-            attn = attn.masked_fill(query_attn_mask[..., None, None, None], 0.0)
-        locations = self._sampling_locations(reference_points, offsets, input_spatial_shapes)
+        lp = levels * points
+        fusable = (proj.is_cuda and proj.dtype == torch.float32 and query_attn_mask is None
+                   and not reference_points.requires_grad and reference_points.shape[-1] in (2, 4)
+                   and lp in (4, 8, 16, 32) and (heads * lp) % 32 == 0)
+        if fusable:
+            # softmax + offset normalisation + reference add in one pass over proj (ms_deform_attn.py:69-82)
+            locations, attn = _SamplingPrep.apply(proj, reference_points, self._float_shapes(input_spatial_shapes, proj),
+                                                  heads, levels, points)
+        else:
+            offsets = proj[..., :n_off].reshape(n, len_q, heads, levels, points, 2)
+            attn = F.softmax(proj[..., n_off:].reshape(n, len_q, heads, lp), -1).view(n, len_q, heads, levels, points)
+            if query_attn_mask is not None:
+                attn = attn.masked_fill(query_attn_mask[..., None, None, None], 0.0)
+            locations = self._sampling_locations(reference_points, offsets, input_spatial_shapes)
 
         if _TILED_ENC and hw is not None and len_q == len_in and value.is_cuda:
             # encoder self-attention: queries are the pixels -> shared-memory tiled forward kernel (opt-in:
