@@ -20,7 +20,7 @@ extern "C" {
 #endif
 
 #define TFB200_E_NULLPTR (-1)
-#define TFB200_E_SHAPE   (-2)   /* C must be a multiple of 128, <= 512 (backward) / 1024 (forward) */
+#define TFB200_E_SHAPE   (-2)   /* C must be a multiple of 4, <= 512 (LayerNorm backward) / 1024 (forward, colsum) */
 #define TFB200_LN_MAX_CTAS 592  /* persistent grid: 148 SMs x 4 CTAs; also the row count of `partial_ws` */
 
 /* number of CTAs (= rows of the [ctas][2][C] fp32 workspace the backward needs) for a problem of `rows` rows */
@@ -39,7 +39,7 @@ int tfb200_add_dropout_layernorm_bwd_f32(const float* dy, const float* s, const 
                                          float* dbranch, float* dgamma, float* dbeta, float* partial_ws,
                                          int64_t rows, int C, float keep_prob, void* stream);
 
-/* out[c] = sum_r x[r][c]  (bias gradient of a Linear over a long token axis); C % 128 == 0, C <= 1024;
+/* out[c] = sum_r x[r][c]  (bias gradient of a Linear over a long token axis); C % 4 == 0, C <= 1024;
  * partial_ws: [tfb200_ln_partial_ctas(rows)][C] fp32.  Deterministic (fixed summation order).                      */
 int tfb200_colsum_f32(const float* x, float* out, float* partial_ws, int64_t rows, int C, void* stream);
 

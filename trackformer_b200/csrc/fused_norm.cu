@@ -14,8 +14,8 @@
 //             ds = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat))
 //             dx = ds;  dbranch = ds * mask * (1/keep);  dgamma = sum_r dy * xhat;  dbeta = sum_r dy
 //
-// One warp owns one row; a lane owns C/32 channels in float4 packs (C % 128 == 0, C <= 1024), so all global
-// accesses are 128-bit and fully coalesced and the row statistics are two warp-shuffle reductions.
+// One warp owns one row; a lane owns float4 packs lane, lane+32, ... (C % 4 == 0, C <= 1024 forward / 512 backward), so
+// all global accesses are 128-bit and coalesced and the row statistics are two warp-shuffle reductions.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -32,22 +32,27 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// PACKS = ceil(C / 128): a lane owns float4 packs lane, lane + 32, ...; packs beyond C/4 are masked, so any C % 4 == 0
+// up to PACKS * 128 works (256 for the shipped models, 288 for the multi-frame TrackFormer configuration).
 template <int PACKS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 add_dropout_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ branch,
                           const uint8_t* __restrict__ mask, const float* __restrict__ gamma,
                           const float* __restrict__ beta, float* __restrict__ s_out, float* __restrict__ y,
-                          float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, float inv_keep,
+                          float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int C, float inv_keep,
                           float eps) {
-  constexpr int C = PACKS * 128;
+  const int npk = C >> 2;
+  const float inv_c = 1.f / float(C);
   const int lane = threadIdx.x & 31;
   const int64_t warp = int64_t(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
   const int64_t nwarps = int64_t(gridDim.x) * kWarpsPerCta;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 ga[PACKS], be[PACKS];
 #pragma unroll
   for (int k = 0; k < PACKS; ++k) {
-    ga[k] = __ldg(reinterpret_cast<const float4*>(gamma) + k * 32 + lane);
-    be[k] = __ldg(reinterpret_cast<const float4*>(beta) + k * 32 + lane);
+    const bool on = k * 32 + lane < npk;
+    ga[k] = on ? __ldg(reinterpret_cast<const float4*>(gamma) + k * 32 + lane) : zero4;
+    be[k] = on ? __ldg(reinterpret_cast<const float4*>(beta) + k * 32 + lane) : zero4;
   }
   for (int64_t r = warp; r < rows; r += nwarps) {
     const float4* xr = reinterpret_cast<const float4*>(x + r * C);
@@ -56,35 +61,42 @@ add_dropout_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__
     float sum = 0.f;
 #pragma unroll
     for (int k = 0; k < PACKS; ++k) {
-      const float4 a = __ldg(xr + k * 32 + lane);
-      float4 b = __ldg(br + k * 32 + lane);
-      if (mask != nullptr) {
-        const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(mask + r * C) + k * 32 + lane);
-        b.x = m.x ? b.x * inv_keep : 0.f;
-        b.y = m.y ? b.y * inv_keep : 0.f;
-        b.z = m.z ? b.z * inv_keep : 0.f;
-        b.w = m.w ? b.w * inv_keep : 0.f;
+      s[k] = zero4;
+      if (k * 32 + lane < npk) {
+        const float4 a = __ldg(xr + k * 32 + lane);
+        float4 b = __ldg(br + k * 32 + lane);
+        if (mask != nullptr) {
+          const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(mask + r * C) + k * 32 + lane);
+          b.x = m.x ? b.x * inv_keep : 0.f;
+          b.y = m.y ? b.y * inv_keep : 0.f;
+          b.z = m.z ? b.z * inv_keep : 0.f;
+          b.w = m.w ? b.w * inv_keep : 0.f;
+        }
+        s[k] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+        sum += (s[k].x + s[k].y) + (s[k].z + s[k].w);
       }
-      s[k] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
-      sum += (s[k].x + s[k].y) + (s[k].z + s[k].w);
     }
-    const float mean = warp_sum(sum) * (1.f / C);
+    const float mean = warp_sum(sum) * inv_c;
     float var = 0.f;
 #pragma unroll
     for (int k = 0; k < PACKS; ++k) {
-      const float dx = s[k].x - mean, dy = s[k].y - mean, dz = s[k].z - mean, dw = s[k].w - mean;
-      var += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      if (k * 32 + lane < npk) {
+        const float dx = s[k].x - mean, dy = s[k].y - mean, dz = s[k].z - mean, dw = s[k].w - mean;
+        var += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+      }
     }
-    const float rstd = rsqrtf(warp_sum(var) * (1.f / C) + eps);
+    const float rstd = rsqrtf(warp_sum(var) * inv_c + eps);
 #pragma unroll
     for (int k = 0; k < PACKS; ++k) {
-      float4 o;
-      o.x = (s[k].x - mean) * rstd * ga[k].x + be[k].x;
-      o.y = (s[k].y - mean) * rstd * ga[k].y + be[k].y;
-      o.z = (s[k].z - mean) * rstd * ga[k].z + be[k].z;
-      o.w = (s[k].w - mean) * rstd * ga[k].w + be[k].w;
-      reinterpret_cast<float4*>(y + r * C)[k * 32 + lane] = o;
-      if (s_out != nullptr) reinterpret_cast<float4*>(s_out + r * C)[k * 32 + lane] = s[k];
+      if (k * 32 + lane < npk) {
+        float4 o;
+        o.x = (s[k].x - mean) * rstd * ga[k].x + be[k].x;
+        o.y = (s[k].y - mean) * rstd * ga[k].y + be[k].y;
+        o.z = (s[k].z - mean) * rstd * ga[k].z + be[k].z;
+        o.w = (s[k].w - mean) * rstd * ga[k].w + be[k].w;
+        reinterpret_cast<float4*>(y + r * C)[k * 32 + lane] = o;
+        if (s_out != nullptr) reinterpret_cast<float4*>(s_out + r * C)[k * 32 + lane] = s[k];
+      }
     }
     if (lane == 0 && mean_out != nullptr) {
       mean_out[r] = mean;
@@ -99,19 +111,22 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s, const uint8_t* __restrict__ mask,
                           const float* __restrict__ gamma, const float* __restrict__ mean_in,
                           const float* __restrict__ rstd_in, float* __restrict__ dx, float* __restrict__ dbranch,
-                          float* __restrict__ partial, int64_t rows, float inv_keep) {
-  constexpr int C = PACKS * 128;
-  __shared__ float red[kWarpsPerCta][2][C];
+                          float* __restrict__ partial, int64_t rows, int C, float inv_keep) {
+  constexpr int CP = PACKS * 128;                  // padded width of the shared reduction buffer
+  __shared__ float red[kWarpsPerCta][2][CP];
+  const int npk = C >> 2;
+  const float inv_c = 1.f / float(C);
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   const int64_t warp = int64_t(blockIdx.x) * kWarpsPerCta + wid;
   const int64_t nwarps = int64_t(gridDim.x) * kWarpsPerCta;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 ga[PACKS], dg[PACKS], db[PACKS];
 #pragma unroll
   for (int k = 0; k < PACKS; ++k) {
-    ga[k] = __ldg(reinterpret_cast<const float4*>(gamma) + k * 32 + lane);
-    dg[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ga[k] = (k * 32 + lane < npk) ? __ldg(reinterpret_cast<const float4*>(gamma) + k * 32 + lane) : zero4;
+    dg[k] = zero4;
+    db[k] = zero4;
   }
   for (int64_t r = warp; r < rows; r += nwarps) {
     const float mean = __ldg(mean_in + r), rstd = __ldg(rstd_in + r);
@@ -119,34 +134,40 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict_
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
     for (int k = 0; k < PACKS; ++k) {
-      const float4 d = __ldg(reinterpret_cast<const float4*>(dy + r * C) + k * 32 + lane);
-      const float4 sv = __ldg(reinterpret_cast<const float4*>(s + r * C) + k * 32 + lane);
-      xh[k] = make_float4((sv.x - mean) * rstd, (sv.y - mean) * rstd, (sv.z - mean) * rstd, (sv.w - mean) * rstd);
-      g[k] = make_float4(d.x * ga[k].x, d.y * ga[k].y, d.z * ga[k].z, d.w * ga[k].w);
-      dg[k].x += d.x * xh[k].x; dg[k].y += d.y * xh[k].y; dg[k].z += d.z * xh[k].z; dg[k].w += d.w * xh[k].w;
-      db[k].x += d.x; db[k].y += d.y; db[k].z += d.z; db[k].w += d.w;
-      sg += (g[k].x + g[k].y) + (g[k].z + g[k].w);
-      sgx += (g[k].x * xh[k].x + g[k].y * xh[k].y) + (g[k].z * xh[k].z + g[k].w * xh[k].w);
+      g[k] = zero4;
+      xh[k] = zero4;
+      if (k * 32 + lane < npk) {
+        const float4 d = __ldg(reinterpret_cast<const float4*>(dy + r * C) + k * 32 + lane);
+        const float4 sv = __ldg(reinterpret_cast<const float4*>(s + r * C) + k * 32 + lane);
+        xh[k] = make_float4((sv.x - mean) * rstd, (sv.y - mean) * rstd, (sv.z - mean) * rstd, (sv.w - mean) * rstd);
+        g[k] = make_float4(d.x * ga[k].x, d.y * ga[k].y, d.z * ga[k].z, d.w * ga[k].w);
+        dg[k].x += d.x * xh[k].x; dg[k].y += d.y * xh[k].y; dg[k].z += d.z * xh[k].z; dg[k].w += d.w * xh[k].w;
+        db[k].x += d.x; db[k].y += d.y; db[k].z += d.z; db[k].w += d.w;
+        sg += (g[k].x + g[k].y) + (g[k].z + g[k].w);
+        sgx += (g[k].x * xh[k].x + g[k].y * xh[k].y) + (g[k].z * xh[k].z + g[k].w * xh[k].w);
+      }
     }
-    const float mg = warp_sum(sg) * (1.f / C);
-    const float mgx = warp_sum(sgx) * (1.f / C);
+    const float mg = warp_sum(sg) * inv_c;
+    const float mgx = warp_sum(sgx) * inv_c;
 #pragma unroll
     for (int k = 0; k < PACKS; ++k) {
-      float4 ds;
-      ds.x = rstd * (g[k].x - mg - xh[k].x * mgx);
-      ds.y = rstd * (g[k].y - mg - xh[k].y * mgx);
-      ds.z = rstd * (g[k].z - mg - xh[k].z * mgx);
-      ds.w = rstd * (g[k].w - mg - xh[k].w * mgx);
-      reinterpret_cast<float4*>(dx + r * C)[k * 32 + lane] = ds;
-      if (dbranch != nullptr) {
-        if (mask != nullptr) {
-          const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(mask + r * C) + k * 32 + lane);
-          ds.x = m.x ? ds.x * inv_keep : 0.f;
-          ds.y = m.y ? ds.y * inv_keep : 0.f;
-          ds.z = m.z ? ds.z * inv_keep : 0.f;
-          ds.w = m.w ? ds.w * inv_keep : 0.f;
+      if (k * 32 + lane < npk) {
+        float4 ds;
+        ds.x = rstd * (g[k].x - mg - xh[k].x * mgx);
+        ds.y = rstd * (g[k].y - mg - xh[k].y * mgx);
+        ds.z = rstd * (g[k].z - mg - xh[k].z * mgx);
+        ds.w = rstd * (g[k].w - mg - xh[k].w * mgx);
+        reinterpret_cast<float4*>(dx + r * C)[k * 32 + lane] = ds;
+        if (dbranch != nullptr) {
+          if (mask != nullptr) {
+            const uchar4 m = __ldg(reinterpret_cast<const uchar4*>(mask + r * C) + k * 32 + lane);
+            ds.x = m.x ? ds.x * inv_keep : 0.f;
+            ds.y = m.y ? ds.y * inv_keep : 0.f;
+            ds.z = m.z ? ds.z * inv_keep : 0.f;
+            ds.w = m.w ? ds.w * inv_keep : 0.f;
+          }
+          reinterpret_cast<float4*>(dbranch + r * C)[k * 32 + lane] = ds;
         }
-        reinterpret_cast<float4*>(dbranch + r * C)[k * 32 + lane] = ds;
       }
     }
   }
@@ -192,9 +213,10 @@ column_partials_finish_kernel(const float* __restrict__ partial, float* __restri
 // LayerNorm backward, partial[blockIdx][c].
 template <int PACKS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-colsum_kernel(const float* __restrict__ x, float* __restrict__ partial, int64_t rows) {
-  constexpr int C = PACKS * 128;
-  __shared__ float red[kWarpsPerCta][C];
+colsum_kernel(const float* __restrict__ x, float* __restrict__ partial, int64_t rows, int C) {
+  constexpr int CP = PACKS * 128;
+  __shared__ float red[kWarpsPerCta][CP];
+  const int npk = C >> 2;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int64_t warp = int64_t(blockIdx.x) * kWarpsPerCta + wid;
   const int64_t nwarps = int64_t(gridDim.x) * kWarpsPerCta;
@@ -204,8 +226,10 @@ colsum_kernel(const float* __restrict__ x, float* __restrict__ partial, int64_t 
   for (int64_t r = warp; r < rows; r += nwarps) {
 #pragma unroll
     for (int k = 0; k < PACKS; ++k) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C) + k * 32 + lane);
-      acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+      if (k * 32 + lane < npk) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + r * C) + k * 32 + lane);
+        acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+      }
     }
   }
 #pragma unroll
@@ -277,20 +301,20 @@ int tfb200_add_dropout_layernorm_fwd_f32(const float* x, const float* branch, co
                                          float* mean, float* rstd, int64_t rows, int C, float keep_prob, float eps,
                                          void* stream) {
   if (!x || !branch || !gamma || !beta || !y) return TFB200_E_NULLPTR;
-  if (rows < 0 || C <= 0 || C % 128 != 0 || C > 128 * kMaxPacks) return TFB200_E_SHAPE;
+  if (rows < 0 || C <= 0 || C % 4 != 0 || C > 128 * kMaxPacks) return TFB200_E_SHAPE;
   if (rows == 0) return 0;
   const float inv_keep = keep_mask ? 1.f / keep_prob : 1.f;
   const int grid = grid_for(rows);
   cudaStream_t st = cudaStream_t(stream);
 #define TFB200_FWD(P)                                                                                          \
   add_dropout_ln_fwd_kernel<P><<<grid, kWarpsPerCta * 32, 0, st>>>(x, branch, keep_mask, gamma, beta, s_out, y, \
-                                                                   mean, rstd, rows, inv_keep, eps)
-  switch (C / 128) {
+                                                                   mean, rstd, rows, C, inv_keep, eps)
+  switch ((C + 127) / 128) {
     case 1: TFB200_FWD(1); break;
     case 2: TFB200_FWD(2); break;
     case 3: TFB200_FWD(3); break;
     case 4: TFB200_FWD(4); break;
-    case 8: TFB200_FWD(8); break;
+    case 5: case 6: case 7: case 8: TFB200_FWD(8); break;
     default: return TFB200_E_SHAPE;
   }
 #undef TFB200_FWD
@@ -302,7 +326,7 @@ int tfb200_add_dropout_layernorm_bwd_f32(const float* dy, const float* s, const 
                                          float* dbranch, float* dgamma, float* dbeta, float* partial_ws,
                                          int64_t rows, int C, float keep_prob, void* stream) {
   if (!dy || !s || !gamma || !mean || !rstd || !dx || !dgamma || !dbeta || !partial_ws) return TFB200_E_NULLPTR;
-  if (rows < 0 || C <= 0 || C % 128 != 0 || C > 128 * kMaxPacks) return TFB200_E_SHAPE;
+  if (rows < 0 || C <= 0 || C % 4 != 0 || C > 512) return TFB200_E_SHAPE;
   cudaStream_t st = cudaStream_t(stream);
   if (rows == 0) {
     cudaMemsetAsync(dgamma, 0, sizeof(float) * C, st);
@@ -313,8 +337,8 @@ int tfb200_add_dropout_layernorm_bwd_f32(const float* dy, const float* s, const 
   const int grid = grid_for(rows);
 #define TFB200_BWD(P)                                                                                           \
   add_dropout_ln_bwd_kernel<P><<<grid, kWarpsPerCta * 32, 0, st>>>(dy, s, keep_mask, gamma, mean, rstd, dx, dbranch, \
-                                                                   partial_ws, rows, inv_keep)
-  switch (C / 128) {
+                                                                   partial_ws, rows, C, inv_keep)
+  switch ((C + 127) / 128) {
     case 1: TFB200_BWD(1); break;
     case 2: TFB200_BWD(2); break;
     case 3: TFB200_BWD(3); break;
@@ -328,20 +352,20 @@ int tfb200_add_dropout_layernorm_bwd_f32(const float* dy, const float* s, const 
 
 int tfb200_colsum_f32(const float* x, float* out, float* partial_ws, int64_t rows, int C, void* stream) {
   if (!x || !out || !partial_ws) return TFB200_E_NULLPTR;
-  if (rows < 0 || C <= 0 || C % 128 != 0 || C > 128 * kMaxPacks) return TFB200_E_SHAPE;
+  if (rows < 0 || C <= 0 || C % 4 != 0 || C > 128 * kMaxPacks) return TFB200_E_SHAPE;
   cudaStream_t st = cudaStream_t(stream);
   if (rows == 0) {
     cudaMemsetAsync(out, 0, sizeof(float) * C, st);
     return int(cudaGetLastError());
   }
   const int grid = grid_for(rows);
-#define TFB200_CS(P) colsum_kernel<P><<<grid, kWarpsPerCta * 32, 0, st>>>(x, partial_ws, rows)
-  switch (C / 128) {
+#define TFB200_CS(P) colsum_kernel<P><<<grid, kWarpsPerCta * 32, 0, st>>>(x, partial_ws, rows, C)
+  switch ((C + 127) / 128) {
     case 1: TFB200_CS(1); break;
     case 2: TFB200_CS(2); break;
     case 3: TFB200_CS(3); break;
     case 4: TFB200_CS(4); break;
-    case 8: TFB200_CS(8); break;
+    case 5: case 6: case 7: case 8: TFB200_CS(8); break;
     default: return TFB200_E_SHAPE;
   }
 #undef TFB200_CS

@@ -177,7 +177,7 @@ std::vector<at::Tensor> add_dropout_layernorm_forward(const at::Tensor& x, const
       xc.data_ptr<float>(), bc.data_ptr<float>(), mptr, g.data_ptr<float>(), b.data_ptr<float>(), s.data_ptr<float>(),
       y.data_ptr<float>(), mean.data_ptr<float>(), rstd.data_ptr<float>(), rows, int(C), float(keep_prob), float(eps),
       c10::cuda::getCurrentCUDAStream().stream());
-  TORCH_CHECK(rc == 0, "add_dropout_layernorm_forward failed (code ", rc, "): C must be a multiple of 128 and <= 512");
+  TORCH_CHECK(rc == 0, "add_dropout_layernorm_forward failed (code ", rc, "): C must be a multiple of 4 and <= 512");
   return {y, s, mean, rstd};
 }
 
@@ -218,7 +218,7 @@ at::Tensor colsum(const at::Tensor& x) {
   at::Tensor ws = at::empty({tfb200_ln_partial_ctas(rows), C}, xc.options());
   const int rc = tfb200_colsum_f32(xc.data_ptr<float>(), out.data_ptr<float>(), ws.data_ptr<float>(), rows, int(C),
                                    c10::cuda::getCurrentCUDAStream().stream());
-  TORCH_CHECK(rc == 0, "colsum failed (code ", rc, "): C must be a multiple of 128 and <= 1024");
+  TORCH_CHECK(rc == 0, "colsum failed (code ", rc, "): C must be a multiple of 4 and <= 1024");
   return out;
 }
 
