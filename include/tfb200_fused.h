@@ -72,6 +72,13 @@ int tfb200_sampling_prep_bwd_f32(const float* grad_loc, const float* grad_attn, 
 int tfb200_lsa_f32(const float* cost, const int* offsets_dev, int64_t* src, int64_t* tgt, int K, int B, int Q, int T,
                    int max_targets, int* status_dev, void* stream);
 
+/* Detection post-processing for the online tracker (deformable_detr.py:286-334 + the per-track read-backs of
+ * tracker.py:306-330): logits [N][Q][C], boxes [N][Q][4] (cx, cy, w, h normalised), sizes_hw [N][2] int64 (h, w) on the
+ * DEVICE  ->  packed [N][Q][6] = {sigmoid score of the best class, its index, x0, y0, x1, y1 in pixels (unclipped)} and,
+ * optionally, labels [N][Q] int64.  Ties between classes resolve to the smallest index (torch.max).                 */
+int tfb200_detect_postprocess_f32(const float* logits, const float* boxes, const int64_t* sizes_hw, float* packed,
+                                  int64_t* labels, int N, int Q, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -296,6 +296,24 @@ std::vector<at::Tensor> lsa(const at::Tensor& cost, const at::Tensor& offsets, i
   return {src, tgt, status};
 }
 
+// ---- detection post-processing for the tracker (deformable_detr.py:286-334) ------------------------------------------
+std::vector<at::Tensor> detect_postprocess(const at::Tensor& logits, const at::Tensor& boxes, const at::Tensor& sizes_hw) {
+  TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == at::kFloat && logits.dim() == 3, "detect_postprocess: logits must be [N,Q,C] fp32 CUDA");
+  TORCH_CHECK(boxes.is_cuda() && boxes.scalar_type() == at::kFloat && boxes.dim() == 3 && boxes.size(2) == 4, "detect_postprocess: boxes must be [N,Q,4] fp32 CUDA");
+  TORCH_CHECK(sizes_hw.is_cuda() && sizes_hw.scalar_type() == at::kLong && sizes_hw.dim() == 2 && sizes_hw.size(1) == 2, "detect_postprocess: sizes must be [N,2] int64 CUDA");
+  const int64_t N = logits.size(0), Q = logits.size(1), C = logits.size(2);
+  TORCH_CHECK(boxes.size(0) == N && boxes.size(1) == Q && sizes_hw.size(0) == N, "detect_postprocess: shape mismatch");
+  c10::cuda::CUDAGuard guard(logits.device());
+  auto lg = logits.contiguous(), bx = boxes.contiguous(), sz = sizes_hw.contiguous();
+  auto packed = at::empty({N, Q, 6}, lg.options());
+  auto labels = at::empty({N, Q}, lg.options().dtype(at::kLong));
+  const int rc = tfb200_detect_postprocess_f32(lg.data_ptr<float>(), bx.data_ptr<float>(), sz.data_ptr<int64_t>(),
+                                               packed.data_ptr<float>(), labels.data_ptr<int64_t>(), int(N), int(Q), int(C),
+                                               at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "detect_postprocess failed (code ", rc, ")");
+  return {packed, labels};
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200 (sm_100a) multi-scale deformable attention; drop-in for the reference extension";
   m.def("ms_deform_attn_forward", &ms_deform_attn_forward, "ms_deform_attn_forward");
@@ -313,4 +331,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("sampling_prep_backward", &sampling_prep_backward);
   m.def("relu_dropout_forward", &relu_dropout_forward);
   m.def("relu_dropout_backward", &relu_dropout_backward);
+  m.def("detect_postprocess", &detect_postprocess);
 }

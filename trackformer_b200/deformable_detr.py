@@ -202,17 +202,32 @@ class DeformableDETR(DETR):
 
 
 class DeformablePostProcess(nn.Module):
-    """Sigmoid scores, best class per query, boxes scaled to the target sizes (deformable_detr.py:286-334)."""
+    """Sigmoid scores, best class per query, boxes scaled to the target sizes (deformable_detr.py:286-334).
+
+    On CUDA the whole chain is one launch of the fused kernel (csrc/track_post.cu); `packed()` exposes its
+    [N, Q, 6] rows {score, label, x0, y0, x1, y1} so the tracker needs a single device->host copy per frame."""
 
     @torch.no_grad()
-    def forward(self, outputs, target_sizes, results_mask=None):
+    def packed(self, outputs, target_sizes):
         logits, boxes = outputs["pred_logits"], outputs["pred_boxes"]
         assert len(logits) == len(target_sizes) and target_sizes.shape[1] == 2
+        if logits.is_cuda and logits.dtype == torch.float32:
+            from .ext import load
+            rows, labels = load().detect_postprocess(logits, boxes, target_sizes.to(logits.device, torch.int64))
+            rows._labels = labels
+            return rows
         scores, labels = logits.sigmoid().max(-1)
         img_h, img_w = target_sizes.unbind(1)
         xyxy = box_cxcywh_to_xyxy(boxes) * torch.stack([img_w, img_h, img_w, img_h], dim=1)[:, None, :]
-        results = [{"scores": s, "scores_no_object": 1 - s, "labels": l, "boxes": b}
-                   for s, l, b in zip(scores, labels, xyxy)]
+        rows = torch.cat([scores[..., None], labels[..., None].to(scores.dtype), xyxy.to(scores.dtype)], -1)
+        rows._labels = labels
+        return rows
+
+    @torch.no_grad()
+    def forward(self, outputs, target_sizes, results_mask=None):
+        rows = self.packed(outputs, target_sizes)
+        results = [{"scores": r[:, 0], "scores_no_object": 1 - r[:, 0], "labels": l, "boxes": r[:, 2:6]}
+                   for r, l in zip(rows, rows._labels)]
         if results_mask is not None:
             for i, keep in enumerate(results_mask):
                 results[i] = {k: v[keep] for k, v in results[i].items()}
