@@ -126,3 +126,29 @@ def test_many_tracks_grow_the_bank():
     # embeddings followed their tracks through the growth of the bank
     for t in tr.tracks:
         assert float(t.hs_embed[-1][0]) == float(t.obj_ind.item())
+
+
+@pytest.mark.parametrize("name,multi_frame", [("model_sequence", False), ("model_sequence_multi_frame", True)])
+def test_tracker_over_the_real_detector_matches_reference(name, multi_frame, monkeypatch):
+    """Reference Tracker + reference tracking model vs ours + ours on a 5-frame random 'video' (canonical weights, CPU,
+    the CUDA op replaced by the oracle's torch restatement).  Thresholds sit in gaps of the score distribution; the
+    fixture records the smallest |score - threshold| of the run, which must dwarf the model-level fp32 noise."""
+    from oracle.torch_ref import msda_core_torch
+    import trackformer_b200.msda_module as mm
+    from test_model_parity_cpu import build
+
+    class _OracleFn:
+        @staticmethod
+        def apply(value, shapes, loc, attn, step):
+            return msda_core_torch(value, shapes, loc, attn)
+    monkeypatch.setattr(mm, "MSDeformAttnFunction", _OracleFn)
+    gold = np.load(os.path.join(GOLD, f"tracker_{name}.npz"))
+    assert gold["margin"] > 1e-5
+    cfg = {k: float(v) for k, v in zip(gold["cfg_keys"], gold["cfg_values"])}
+    cfg["prev_frame_dist"] = int(cfg["prev_frame_dist"])
+    out = tf.run_model_sequence(build, Tracker, DeformablePostProcess(), cfg, multi_frame=multi_frame)
+    for key in ("num_reids", "track_num", "frame_index", "active_ids", "inactive_ids", "inactive_counts"):
+        np.testing.assert_array_equal(out[key], gold[key], err_msg=key)
+    assert out["rows"].shape == gold["rows"].shape
+    np.testing.assert_array_equal(out["rows"][:, :3], gold["rows"][:, :3])
+    np.testing.assert_allclose(out["rows"][:, 3:], gold["rows"][:, 3:], rtol=1e-3, atol=1e-3)

@@ -205,3 +205,51 @@ def run_case(tracker_cls, post, case, device="cpu", seed=0):
     width = max(len(p) for p in per_frame)
     out["per_frame_ids"] = np.asarray([p + [-2] * (width - len(p)) for p in per_frame], np.int64)
     return out
+
+
+# ---------------------------------------------------------------------------------- the real detector under the tracker
+def model_frames(size, n_frames, seed=5):
+    """A slowly changing random 'video': base image plus a growing perturbation."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.randn(3, *size, generator=g)
+    drift = torch.randn(3, *size, generator=g)
+    return [base + 0.03 * t * drift for t in range(n_frames)]
+
+
+class _ScoreLog:
+    """Wraps a post-processor and records every score / label it hands to the tracker (to measure decision margins)."""
+
+    def __init__(self, post):
+        self.post, self.scores, self.labels = post, [], []
+
+    def __call__(self, outputs, sizes):
+        res = self.post(outputs, sizes)
+        self.scores.append(res[0]["scores"].detach().cpu().numpy().copy())
+        self.labels.append(res[0]["labels"].detach().cpu().numpy().copy())
+        return res
+
+
+def run_model_sequence(build, tracker_cls, post, cfg_overrides, size=(128, 160), n_frames=5, device="cpu",
+                       multi_frame=False, log_scores=False):
+    import model_fixtures as mf
+    model, _ = build(True, multi_frame)
+    mf.canonical_weights_(model, 0)
+    with torch.no_grad():                      # random weights favour an arbitrary class: make it class 0 ("person")
+        for name, p in model.named_parameters():
+            if "class_embed" in name and name.endswith("bias"):
+                p[0] += 6.0
+    model.to(device)
+    model.tracking()
+    cfg = dict(BASE_CFG)
+    cfg.update(cfg_overrides)
+    post = _ScoreLog(post) if log_scores else post
+    tracker = tracker_cls(model, {"bbox": post}, cfg, False)
+    tracker.reset()
+    for frame in model_frames(size, n_frames):
+      with torch.no_grad():                     # src/track.py runs the tracker under no_grad
+        tracker.step({"img": frame[None], "orig_size": torch.tensor([[size[0] * 4, size[1] * 4]]),
+                      "dets": torch.zeros(1, 0, 4)})
+    out = summarise(tracker)
+    if log_scores:
+        out["_scores"], out["_labels"] = post.scores, post.labels
+    return out
