@@ -132,10 +132,14 @@ class DeformableTransformerDecoderLayer(nn.Module):
         return add_dropout_layernorm(tgt, ff, self.dropout4, self.norm3)
 
     def forward(self, tgt, query_pos, reference_points, src, src_spatial_shapes, src_padding_mask=None,
-                query_attn_mask=None):
-        # query self-attention (dense, tiny: Lq <= ~800) -- sequence-first nn.MultiheadAttention like the reference
+                query_attn_mask=None, padded_queries=None):
+        # query self-attention (dense, tiny: Lq <= ~800) -- sequence-first nn.MultiheadAttention like the reference.
+        # padded_queries [N, Lq] marks filler queries (fixed-shape CUDA-graph replays, graphed_detector.py): they are
+        # hidden from the real queries as attention KEYS, which is all it takes for the real rows to be unaffected
+        # (every other decoder op is row-wise).
         qk = _add_pos(tgt, query_pos).transpose(0, 1)
-        sa = self.self_attn(qk, qk, tgt.transpose(0, 1), key_padding_mask=query_attn_mask)[0].transpose(0, 1)
+        key_mask = query_attn_mask if padded_queries is None else padded_queries
+        sa = self.self_attn(qk, qk, tgt.transpose(0, 1), key_padding_mask=key_mask)[0].transpose(0, 1)
         tgt = add_dropout_layernorm(tgt, sa, self.dropout2, self.norm2)
         # deformable cross-attention into the encoder memory
         ca = self.cross_attn(_add_pos(tgt, query_pos), reference_points, src, src_spatial_shapes,
@@ -154,7 +158,7 @@ class DeformableTransformerDecoder(nn.Module):
         self.class_embed = None
 
     def forward(self, tgt, reference_points, src, src_spatial_shapes, src_valid_ratios, query_pos=None,
-                src_padding_mask=None, query_attn_mask=None):
+                src_padding_mask=None, query_attn_mask=None, padded_queries=None):
         out = tgt
         hs, refs = [], []
         for lid, layer in enumerate(self.layers):
@@ -163,7 +167,8 @@ class DeformableTransformerDecoder(nn.Module):
             else:
                 assert reference_points.shape[-1] == 2
                 ref_in = reference_points[:, :, None] * src_valid_ratios[:, None]
-            out = layer(out, query_pos, ref_in, src, src_spatial_shapes, src_padding_mask, query_attn_mask)
+            out = layer(out, query_pos, ref_in, src, src_spatial_shapes, src_padding_mask, query_attn_mask,
+                        padded_queries)
 
             if self.bbox_embed is not None:     # refine the reference boxes for the next layer; no gradient through them
                 delta = self.bbox_embed[lid](out)
@@ -274,6 +279,7 @@ class DeformableTransformer(nn.Module):
         query_pos = query_pos.unsqueeze(0).expand(bs, -1, -1)
         tgt = tgt.unsqueeze(0).expand(bs, -1, -1)
         reference_points = self.reference_points(query_pos).sigmoid()
+        padded_queries = None
 
         if targets is not None and "track_query_hs_embeds" in targets[0]:
             # track queries: previous-frame output embeddings as content, zero positional part, previous box
@@ -283,10 +289,14 @@ class DeformableTransformer(nn.Module):
             query_pos = torch.cat([torch.zeros_like(prev_hs), query_pos], dim=1)
             tgt = torch.cat([prev_hs, tgt], dim=1)
             reference_points = torch.cat([prev_boxes[..., :2], reference_points], dim=1)
+            if "track_query_padding" in targets[0]:
+                # [K] bool per image, True = filler track query (not in the reference: used by GraphedDetector)
+                filler = torch.stack([t["track_query_padding"] for t in targets])
+                padded_queries = torch.cat([filler, filler.new_zeros(bs, tgt.shape[1] - filler.shape[1])], dim=1)
         init_reference = reference_points
 
         hs, inter_references = self.decoder(tgt, reference_points, memory, spatial_shapes, valid_ratios,
-                                            query_pos, enc_mask, None)
+                                            query_pos, enc_mask, None, padded_queries)
         return hs, memory, init_reference, inter_references, None, None
 
 
