@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=1)
     ap.add_argument("--no-tf32", action="store_true", help="strict fp32 GEMMs/convs (default: TF32 tensor cores)")
     ap.add_argument("--no-optimizer", action="store_true")
+    ap.add_argument("--torch-adamw", action="store_true", help="torch.optim.AdamW(fused=True) instead of the flat kernel")
     ap.add_argument("--no-graphs", action="store_true", help="eager step instead of CUDA-graph replay")
     ap.add_argument("--two-graphs", action="store_true",
                     help="forward graph + eager loss + backward graph instead of the single full-step graph")
@@ -234,10 +235,15 @@ def main():
     dev_frames = host_frames.to(dev)
     targets = make_targets(bpg, dev, 2 + rank)
 
-    opt_factory = None if args.no_optimizer else (
-        lambda ps: torch.optim.AdamW(ps, lr=2e-4, weight_decay=1e-4, fused=True))
+    opt_factory = flat = None
+    if args.torch_adamw and not args.no_optimizer:
+        opt_factory = lambda ps: torch.optim.AdamW(ps, lr=2e-4, weight_decay=1e-4, fused=True)    # noqa: E731
+    elif not args.no_optimizer:
+        # the reference's three learning-rate groups (src/train.py:100-119), updated by the one-pass clip + AdamW kernel
+        from trackformer_b200.flat_adamw import reference_param_groups
+        flat = {"groups": reference_param_groups(model)}
     step = TrainStep(model, criterion, opt_factory, max_norm=0.1, use_graphs=not args.no_graphs,
-                     example_frames=dev_frames, example_targets=None if args.two_graphs else targets)
+                     example_frames=dev_frames, example_targets=None if args.two_graphs else targets, flat_adamw=flat)
 
     def barrier():
         if world > 1:
@@ -363,7 +369,7 @@ def main():
         "config": {"workload": workload, "global_batch": bpg * world, "parallelism": f"dp{world}",
                    "dense_math": "TF32 tensor cores (cuDNN/cuBLAS), fp32 accumulate" if tf32 else "strict fp32",
                    "msda_math": "fp32 (hand-written sm_100a kernels)", "dropout": 0.1,
-                   "optimizer": "none" if args.no_optimizer else "AdamW(fused) + clip_grad_norm 0.1",
+                   "optimizer": "none" if args.no_optimizer else ("torch AdamW(fused)" if args.torch_adamw else "flat one-pass AdamW kernel, reference lr groups") + " + clip_grad_norm 0.1",
                    "execution": "eager" if args.no_graphs else
                    ("forward graph + loss (device Hungarian matching, no host sync) + backward graph" if args.two_graphs else
                     "ONE CUDA graph per step: forward + matching cost + device Hungarian matching (csrc/lsa.cu) + loss + "

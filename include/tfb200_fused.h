@@ -79,6 +79,14 @@ int tfb200_lsa_f32(const float* cost, const int* offsets_dev, int64_t* src, int6
 int tfb200_detect_postprocess_f32(const float* logits, const float* boxes, const int64_t* sizes_hw, float* packed,
                                   int64_t* labels, int N, int Q, int C, void* stream);
 
+/* clip_grad_norm_ + AdamW (decoupled weight decay) over one contiguous fp32 range of n parameters in one pass
+ * (engine.py:147-151 + torch.optim.AdamW of train.py:118).  grad_norm_dev: device scalar holding the global gradient
+ * 2-norm, or NULL for no clipping; the clip coefficient min(1, max_norm / (norm + 1e-6)) is applied on the fly, the
+ * gradient buffer is not modified.  step >= 1 is the update count (bias correction).  Pointers 16-byte aligned.      */
+int tfb200_flat_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                          const float* grad_norm_dev, float max_norm, float lr, float beta1, float beta2, float eps,
+                          float weight_decay, int64_t step, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,12 +96,17 @@ def test_graph_replay_matches_eager_tracker(dev, multi_frame):
     from trackformer_b200.tracker import Tracker
     build, size = _build(dev), (128, 160)
     thr = _probe_threshold(build, dev, multi_frame, size)
-    cfg = dict(detection_obj_score_thresh=thr, track_obj_score_thresh=thr * 0.96, reid_score_thresh=thr * 0.985,
-               inactive_patience=3, reid_sim_threshold=2.0, detection_nms_thresh=0.7, track_nms_thresh=0.7)
-    eager = tf.run_model_sequence(build, Tracker, DeformablePostProcess(), cfg, size=size, n_frames=6, device=dev,
-                                  multi_frame=multi_frame, log_scores=True)
-    margin = min(float(np.abs(np.concatenate(eager["_scores"]) - t).min())
-                 for t in (cfg["detection_obj_score_thresh"], cfg["track_obj_score_thresh"], cfg["reid_score_thresh"]))
+    best = None
+    for f_track, f_reid in ((0.96, 0.985), (0.97, 0.99), (0.975, 1.0), (0.95, 0.98), (0.98, 0.995), (0.965, 1.01)):
+        cfg = dict(detection_obj_score_thresh=thr, track_obj_score_thresh=thr * f_track, reid_score_thresh=thr * f_reid,
+                   inactive_patience=3, reid_sim_threshold=2.0, detection_nms_thresh=0.7, track_nms_thresh=0.7)
+        eager = tf.run_model_sequence(build, Tracker, DeformablePostProcess(), cfg, size=size, n_frames=6, device=dev,
+                                      multi_frame=multi_frame, log_scores=True)
+        margin = min(float(np.abs(np.concatenate(eager["_scores"]) - t).min())
+                     for t in (cfg["detection_obj_score_thresh"], cfg["track_obj_score_thresh"], cfg["reid_score_thresh"]))
+        if best is None or margin > best[0]:
+            best = (margin, cfg, eager)
+    margin, cfg, eager = best
     detectors = []
 
     class GraphTracker(Tracker):
@@ -113,7 +118,7 @@ def test_graph_replay_matches_eager_tracker(dev, multi_frame):
     det = detectors[0]
     assert det.replays == 6 and 1 <= det.captures <= 6
     assert len(eager["rows"]) > 0
-    if margin < 1e-4:
+    if margin < 1.5e-5:
         pytest.skip(f"eager run has a decision {margin:.1e} from its threshold: ids may legitimately differ")
     for key in ("num_reids", "track_num", "active_ids", "inactive_ids"):
         np.testing.assert_array_equal(graphed[key], eager[key], err_msg=key)
@@ -126,6 +131,7 @@ def test_graph_replay_outputs_match_eager_forward(dev):
     from trackformer_b200.graphed_detector import GraphedDetector
     model, _ = _build(dev)(True, False)
     mf.canonical_weights_(model, 0)
+    model.to(dev)
     model.tracking()
     f1, f2 = (f.to(dev) for f in tf.model_frames((160, 224), 2))
     with torch.no_grad():

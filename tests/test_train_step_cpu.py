@@ -1,0 +1,39 @@
+"""Host-side logic of the flat parameter layout (TrainStep(flat_adamw=...)) on CPU: parameters move into one buffer
+without changing the model; the update itself is CUDA-only and must refuse CPU tensors loudly."""
+import pytest
+import torch
+
+import model_fixtures as mf
+from test_model_parity_cpu import build, oracle_op  # noqa: F401  (fixture)
+
+
+def test_flat_layout_keeps_the_model_and_partitions_groups(oracle_op):
+    from trackformer_b200.flat_adamw import reference_param_groups
+    from trackformer_b200.train_step import TrainStep
+    model, criterion = build(False, False, enc_layers=1, dec_layers=1, num_queries=20, dropout=0.0)
+    mf.canonical_weights_(model, 0)
+    model.eval()
+    x = mf.make_images(3, [(96, 128)])[0][None]
+    with torch.no_grad():
+        before = model(x)[0]["pred_boxes"].clone()
+    groups = reference_param_groups(model)
+    n_trainable = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    assert sum(p.numel() for g in groups for p in g["params"]) == n_trainable
+    step = TrainStep(model, criterion, None, use_graphs=False, flat_adamw={"groups": groups})
+    ranges = step.flat_optimizer.ranges
+    assert [e - b for b, e in ranges] == [sum(p.numel() for p in g["params"]) for g in groups]
+    assert all(b % 4 == 0 for b, _ in ranges) and all(ranges[i][1] <= ranges[i + 1][0] for i in range(len(ranges) - 1))
+    lo, hi = step.flat_param.data_ptr(), step.flat_param.data_ptr() + 4 * step.flat_param.numel()
+    for p in step.params:
+        assert lo <= p.data_ptr() < hi and lo <= p.grad.data_ptr() - step.flat_grad.data_ptr() + lo < hi
+        assert p.grad.stride() == p.stride()
+    with torch.no_grad():
+        after = model(x)[0]["pred_boxes"]
+    assert torch.equal(before, after)
+    # writing through the flat buffer is writing the parameters
+    step.flat_param.zero_()
+    assert all(float(p.detach().abs().sum()) == 0.0 for p in step.params)
+    with pytest.raises(RuntimeError):
+        step.flat_optimizer.step()                       # CUDA-only update: no CPU fallback
+    with pytest.raises(AssertionError):
+        TrainStep(model, criterion, None, use_graphs=False, flat_adamw={"groups": groups[:2]})

@@ -79,3 +79,66 @@ def test_optimizer_step_updates_weights_and_clips(cuda_device):
     assert float(torch.linalg.vector_norm(step.flat_grad)) <= 0.1 * 1.001      # clip_grad_norm_(0.1) semantics
     after = [p for p in model.parameters() if p.requires_grad]
     assert sum(int(not torch.equal(a, b)) for a, b in zip(after, before)) > len(before) // 2
+
+
+@pytest.mark.parametrize("n,clip", [(1 << 20, True), (4099, True), (1023, False), (3, True)])
+def test_flat_adamw_kernel_matches_torch_adamw(cuda_device, n, clip):
+    """clip_grad_norm_ + torch.optim.AdamW vs the one-pass kernel, 4 steps, two lr groups in one flat buffer"""
+    from trackformer_b200.flat_adamw import FlatAdamW
+    dev = cuda_device
+    g = torch.Generator().manual_seed(n)
+    split = (n // 3 + 3) & ~3 if n > 8 else 0
+    p0 = torch.randn(n, generator=g).to(dev)
+    ref_a, ref_b = p0[:split].clone().requires_grad_(True), p0[split:].clone().requires_grad_(True)
+    ref_opt = torch.optim.AdamW([{"params": [ref_a], "lr": 3e-3}, {"params": [ref_b], "lr": 1e-2, "weight_decay": 0.0}],
+                                lr=3e-3, weight_decay=1e-2)
+    flat_p, flat_g = p0.clone(), torch.zeros(n, device=dev)
+    opt = FlatAdamW([{"params": [], "lr": 3e-3, "weight_decay": 1e-2}, {"params": [], "lr": 1e-2, "weight_decay": 0.0}],
+                    [(0, split), (split, n)], flat_p, flat_g)
+    for step in range(4):
+        grad = torch.randn(n, generator=g).to(dev) * (0.5 + step)
+        ref_a.grad, ref_b.grad = grad[:split].clone(), grad[split:].clone()
+        flat_g.copy_(grad)
+        if clip:
+            torch.nn.utils.clip_grad_norm_([ref_a, ref_b], 0.7)
+            opt.step(torch.linalg.vector_norm(flat_g), 0.7)
+            assert torch.equal(flat_g, grad)                     # the gradient buffer itself is left alone
+        else:
+            opt.step()
+        ref_opt.step()
+        torch.testing.assert_close(flat_p, torch.cat([ref_a.detach(), ref_b.detach()]), rtol=2e-6, atol=2e-7)
+    state = opt.state_dict()
+    assert state["steps"] == 4 and state["exp_avg"].shape == (n,)
+
+
+def test_flat_parameter_layout_and_reference_groups(cuda_device):
+    """TrainStep(flat_adamw=...) moves every trainable parameter into one buffer (groups contiguous, 16-byte aligned
+    starts, NHWC filters keep their strides) without changing the model, and trains like torch.optim.AdamW."""
+    from trackformer_b200.flat_adamw import reference_param_groups
+    from trackformer_b200.train_step import TrainStep
+    dev = cuda_device
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    model, criterion = small_model(dev)
+    model_t = copy.deepcopy(model)
+    groups = reference_param_groups(model)
+    assert [g["lr"] for g in groups] == [2e-4, 2e-5, 2e-5] and all(len(g["params"]) for g in groups)
+    names = {id(p): n for n, p in model.named_parameters()}
+    assert all("backbone.0" in names[id(p)] for p in groups[1]["params"])
+    assert all(("sampling_offsets" in names[id(p)]) or ("reference_points" in names[id(p)]) for p in groups[2]["params"])
+    frames = [torch.randn(1, 3, 192, 256, generator=torch.Generator().manual_seed(i)).to(dev) for i in range(3)]
+    flat = TrainStep(model, criterion, None, max_norm=0.1, use_graphs=True, example_frames=frames[0],
+                     flat_adamw={"groups": groups})
+    lo, hi = flat.flat_param.data_ptr(), flat.flat_param.data_ptr() + 4 * flat.flat_param.numel()
+    assert all(lo <= p.data_ptr() < hi for p in flat.params)
+    assert all(b % 4 == 0 for b, _ in flat.flat_optimizer.ranges)
+    assert sum(e - b for b, e in flat.flat_optimizer.ranges) == sum(p.numel() for p in flat.params)
+    groups_t = reference_param_groups(model_t)
+    torch_step = TrainStep(model_t, criterion, lambda ps: torch.optim.AdamW(groups_t, lr=2e-4, weight_decay=1e-4),
+                           max_norm=0.1, use_graphs=True, example_frames=frames[0])
+    for i, f in enumerate(frames):
+        tg = targets_for(dev, 30 + i, 5)
+        torch.testing.assert_close(flat(f, tg), torch_step(f, tg), rtol=2e-4, atol=2e-4)
+    sd, sd_t = model.state_dict(), model_t.state_dict()
+    for k in sd:
+        torch.testing.assert_close(sd[k], sd_t[k], rtol=1e-4, atol=2e-6, msg=k)

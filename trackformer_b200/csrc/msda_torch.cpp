@@ -314,6 +314,27 @@ std::vector<at::Tensor> detect_postprocess(const at::Tensor& logits, const at::T
   return {packed, labels};
 }
 
+// ---- clip + AdamW over a flat parameter range (engine.py:147-151) ---------------------------------------------------
+void flat_adamw(at::Tensor param, const at::Tensor& grad, at::Tensor exp_avg, at::Tensor exp_avg_sq, int64_t begin,
+                int64_t end, const c10::optional<at::Tensor>& grad_norm, double max_norm, double lr, double beta1,
+                double beta2, double eps, double weight_decay, int64_t step) {
+  for (const at::Tensor* t : std::initializer_list<const at::Tensor*>{&param, &grad, &exp_avg, &exp_avg_sq})
+    TORCH_CHECK(t->is_cuda() && t->scalar_type() == at::kFloat && t->dim() == 1 && t->is_contiguous() &&
+                t->numel() == param.numel(), "flat_adamw: buffers must be flat contiguous fp32 CUDA tensors of one length");
+  TORCH_CHECK(0 <= begin && begin <= end && end <= param.numel() && begin % 4 == 0, "flat_adamw: bad range");
+  const float* norm = nullptr;
+  if (grad_norm.has_value()) {
+    TORCH_CHECK(grad_norm->is_cuda() && grad_norm->scalar_type() == at::kFloat && grad_norm->numel() == 1, "flat_adamw: grad_norm must be a CUDA fp32 scalar");
+    norm = grad_norm->data_ptr<float>();
+  }
+  const c10::cuda::CUDAGuard guard(param.device());
+  const int rc = tfb200_flat_adamw_f32(param.data_ptr<float>() + begin, grad.data_ptr<float>() + begin,
+                                       exp_avg.data_ptr<float>() + begin, exp_avg_sq.data_ptr<float>() + begin, end - begin,
+                                       norm, float(max_norm), float(lr), float(beta1), float(beta2), float(eps),
+                                       float(weight_decay), step, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "flat_adamw failed (code ", rc, ")");
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200 (sm_100a) multi-scale deformable attention; drop-in for the reference extension";
   m.def("ms_deform_attn_forward", &ms_deform_attn_forward, "ms_deform_attn_forward");
@@ -332,4 +353,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("relu_dropout_forward", &relu_dropout_forward);
   m.def("relu_dropout_backward", &relu_dropout_backward);
   m.def("detect_postprocess", &detect_postprocess);
+  m.def("flat_adamw", &flat_adamw);
 }

@@ -48,7 +48,10 @@ class TrainStep:
 
     def __init__(self, model, criterion, optimizer_factory=None, max_norm: float = 0.1,
                  use_graphs: bool = True, example_frames: Optional[torch.Tensor] = None,
-                 example_targets: Optional[list] = None):
+                 example_targets: Optional[list] = None, flat_adamw: Optional[dict] = None):
+        """``optimizer_factory(params)`` builds any torch optimizer; ``flat_adamw={'groups': [...], 'betas':..., 'eps':...}``
+        (groups as for torch.optim.AdamW, e.g. flat_adamw.reference_param_groups(model)) instead lays the PARAMETERS out
+        flat as well and updates them with the one-pass clip + AdamW kernel."""
         self.model = model
         self.criterion = criterion
         self.max_norm = max_norm
@@ -63,19 +66,48 @@ class TrainStep:
         self._static_world_boxes = True
         self.g_fwd = self.g_bwd = self.g_full = None
 
-        # flat gradient buffer: param.grad are views -> one zero-fill, one all-reduce, one norm
-        total = sum(p.numel() for p in self.params)
+        # flat layout: groups (if any) are contiguous and start on a 16-byte boundary
+        groups = None
+        if flat_adamw is not None:
+            assert optimizer_factory is None, "give either optimizer_factory or flat_adamw"
+            groups = [dict(g, params=list(g["params"])) for g in flat_adamw["groups"]]
+            ordered = [p for g in groups for p in g["params"]]
+            assert len({id(p) for p in ordered}) == len(ordered) == len(self.params) and \
+                {id(p) for p in ordered} == {id(p) for p in self.params}, "groups must partition the trainable parameters"
+            self.params = ordered
+        offsets, ranges, ofs = [], [], 0
+        for g in (groups or [{"params": self.params}]):
+            begin = ofs = (ofs + 3) & ~3
+            for p in g["params"]:
+                offsets.append(ofs)
+                ofs += p.numel()
+            ranges.append((begin, ofs))
+        total = (ofs + 3) & ~3
         dev = self.params[0].device
-        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
-        ofs = 0
-        for p in self.params:
-            chunk = self.flat_grad[ofs:ofs + p.numel()]
+
+        def flat_view(buf, p, o):
+            chunk = buf[o:o + p.numel()]
             if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
-                o, i, kh, kw = p.shape                  # NHWC filter: the gradient view gets the same strides
-                p.grad = chunk.view(o, kh, kw, i).permute(0, 3, 1, 2)
-            else:
-                p.grad = chunk.view_as(p)
-            ofs += p.numel()
+                co, ci, kh, kw = p.shape                # NHWC filter: the view gets the same strides
+                return chunk.view(co, kh, kw, ci).permute(0, 3, 1, 2)
+            return chunk.view_as(p)
+
+        # flat gradient buffer: param.grad are views -> one zero-fill, one all-reduce, one norm
+        self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, offsets):
+            p.grad = flat_view(self.flat_grad, p, o)
+        self.flat_param = None
+        self.flat_optimizer = None
+        if groups is not None:
+            from .flat_adamw import FlatAdamW
+            self.flat_param = torch.zeros(total, dtype=torch.float32, device=dev)
+            with torch.no_grad():
+                for p, o in zip(self.params, offsets):
+                    view = flat_view(self.flat_param, p, o)
+                    view.copy_(p)
+                    p.data = view                        # the parameter now lives in the flat buffer
+            self.flat_optimizer = FlatAdamW(groups, ranges, self.flat_param, self.flat_grad,
+                                            flat_adamw.get("betas", (0.9, 0.999)), flat_adamw.get("eps", 1e-8))
         self.optimizer = optimizer_factory(self.params) if optimizer_factory is not None else None
         if use_graphs:
             assert example_frames is not None and example_frames.is_cuda
@@ -178,4 +210,7 @@ class TrainStep:
                 norm = torch.linalg.vector_norm(self.flat_grad)
                 self.flat_grad.mul_(torch.clamp(self.max_norm / (norm + 1e-6), max=1.0))
             self.optimizer.step()
+        elif self.flat_optimizer is not None:
+            norm = torch.linalg.vector_norm(self.flat_grad) if self.max_norm > 0 else None
+            self.flat_optimizer.step(norm, self.max_norm)
         return loss.detach()
