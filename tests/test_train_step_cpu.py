@@ -21,7 +21,8 @@ def test_flat_layout_keeps_the_model_and_partitions_groups(oracle_op):
     assert sum(p.numel() for g in groups for p in g["params"]) == n_trainable
     step = TrainStep(model, criterion, None, use_graphs=False, flat_adamw={"groups": groups})
     ranges = step.flat_optimizer.ranges
-    assert [e - b for b, e in ranges] == [sum(p.numel() for p in g["params"]) for g in groups]
+    assert all(e - b >= sum(p.numel() for p in g["params"]) for (b, e), g in zip(ranges, groups))
+    assert all(b % 64 == 0 for b, _ in ranges) and all((p.data_ptr() - step.flat_param.data_ptr()) % 256 == 0 and (p.grad.data_ptr() - step.flat_grad.data_ptr()) % 256 == 0 for p in step.params)
     assert all(b % 4 == 0 for b, _ in ranges) and all(ranges[i][1] <= ranges[i + 1][0] for i in range(len(ranges) - 1))
     lo, hi = step.flat_param.data_ptr(), step.flat_param.data_ptr() + 4 * step.flat_param.numel()
     for p in step.params:

@@ -23,7 +23,7 @@ from torch.autograd.function import once_differentiable
 from . import ext
 
 _MIN_ROWS = 2048          # below this the generic reduction is launch-bound anyway
-_SPLIT_K = os.environ.get("TFB200_WGRAD_SPLITK", "1") != "0"
+_SPLIT_K = os.environ.get("TFB200_WGRAD_SPLITK", "0") == "1"      # opt-in: see weight_grad
 _SM_COUNT = 148
 
 
@@ -33,7 +33,11 @@ def weight_grad(gy2: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
     The product is a small [c_out, c_in] tile grid reduced over tens of thousands of rows; the library GEMM does not
     split that reduction and runs 16-64 CTAs on a 148-SM part (38 us for 256 x 256 x 22223, 76 TFLOP/s).  Splitting
     the token axis into `s` slabs turns it into one batched GEMM with s x as many CTAs plus a [s, c_out, c_in] sum:
-    same products, fp32 accumulation, only the summation order over tokens changes."""
+    same products, fp32 accumulation, only the summation order over tokens changes.
+
+    Measured (tools/wgrad_bench.py, cold L2): 44 -> 32 us for 256 x 256, 55 -> 36 us for 384 x 256; but inside the
+    replayed training step, where the operands were just written and sit in the 126 MB L2, the three launches cost
+    more than the split saves (16.31 ms/step without vs 16.71 ms with), so it is OFF unless TFB200_WGRAD_SPLITK=1."""
     k, c_out = gy2.shape
     c_in = x2.shape[1]
     tiles = -(-c_out // 128) * -(-c_in // 128)

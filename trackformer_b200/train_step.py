@@ -75,14 +75,19 @@ class TrainStep:
             assert len({id(p) for p in ordered}) == len(ordered) == len(self.params) and \
                 {id(p) for p in ordered} == {id(p) for p in self.params}, "groups must partition the trainable parameters"
             self.params = ordered
+        # every tensor starts on a 256-byte boundary: library GEMM / convolution kernels and the vectorised elementwise
+        # kernels need 16-byte aligned operands, and a densely packed buffer would misalign everything behind the first
+        # odd-sized bias (the padding -- < 64 floats per tensor -- stays zero in gradients, parameters and moments)
+        align = 64
         offsets, ranges, ofs = [], [], 0
         for g in (groups or [{"params": self.params}]):
-            begin = ofs = (ofs + 3) & ~3
+            begin = ofs = -(-ofs // align) * align
             for p in g["params"]:
+                ofs = -(-ofs // align) * align
                 offsets.append(ofs)
                 ofs += p.numel()
             ranges.append((begin, ofs))
-        total = (ofs + 3) & ~3
+        total = -(-ofs // align) * align
         dev = self.params[0].device
 
         def flat_view(buf, p, o):
