@@ -296,7 +296,9 @@ def main():
     for _ in range(probe_steps):
         probe(dev_frames, targets)
     torch.cuda.synchronize(dev)
-    launches_per_step = (msda.launch_count() - launches0) // probe_steps
+    launches_per_step = (msda.launch_count() - launches0) // probe_steps       # every kernel of libmsda_b200.so
+    if step.flat_optimizer is not None:
+        launches_per_step += len(step.flat_optimizer.ranges)                     # clip + AdamW, one launch per lr group
     msda_function.set_timing_sink(None)
     launches = launches_per_step * args.steps
 
@@ -375,8 +377,9 @@ def main():
                     "ONE CUDA graph per step: forward + matching cost + device Hungarian matching (csrc/lsa.cu) + loss + "
                     "backward incl. gradient accumulation") + "; flat-buffer gradient all-reduce (NCCL), clip and fused "
                    "AdamW follow the replay",
-                   "gpu_launches_note": f"{launches_per_step} own kernel launches per step "
-                                        "(12 MSDeformAttn forward + 12 backward), replayed from the graphs",
+                   "gpu_launches_note": f"{launches_per_step} own kernel launches per step (12 MSDeformAttn forward + 12 "
+                                        "backward, fused residual+LayerNorm, column sums, ReLU+dropout, sampling prep, "
+                                        "Hungarian matching, clip+AdamW), replayed from the graph except the optimizer",
                    "weights": "random init", "gt_boxes_per_frame": N_GT,
                    "l2": "no explicit flush: one step streams >1 GB of activations/weights, far above the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": host_frames.numel() * 4,

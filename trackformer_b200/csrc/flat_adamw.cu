@@ -13,6 +13,7 @@
 #include <stdint.h>
 
 #include "../../include/tfb200_fused.h"
+#include "launch_counter.h"
 
 namespace {
 
@@ -73,5 +74,6 @@ extern "C" int tfb200_flat_adamw_f32(float* param, const float* grad, float* exp
   if (ctas < 1) ctas = 1;
   flat_adamw_kernel<<<unsigned(ctas), 256, 0, cudaStream_t(stream)>>>(param, grad, exp_avg, exp_avg_sq, n,
                                                                       grad_norm_dev, a);
+  msda_b200_count_launches(1);
   return int(cudaGetLastError());
 }

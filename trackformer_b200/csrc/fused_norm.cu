@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include "../../include/tfb200_fused.h"
+#include "launch_counter.h"
 
 namespace {
 
@@ -318,6 +319,7 @@ int tfb200_add_dropout_layernorm_fwd_f32(const float* x, const float* branch, co
     default: return TFB200_E_SHAPE;
   }
 #undef TFB200_FWD
+  msda_b200_count_launches(1);
   return int(cudaGetLastError());
 }
 
@@ -347,6 +349,7 @@ int tfb200_add_dropout_layernorm_bwd_f32(const float* dy, const float* s, const 
   }
 #undef TFB200_BWD
   column_partials_finish_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial_ws, dgamma, dbeta, grid, 2 * C, C);
+  msda_b200_count_launches(2);
   return int(cudaGetLastError());
 }
 
@@ -370,6 +373,7 @@ int tfb200_colsum_f32(const float* x, float* out, float* partial_ws, int64_t row
   }
 #undef TFB200_CS
   column_partials_finish_kernel<<<(C + 31) / 32, 256, 0, st>>>(partial_ws, out, out, grid, C, C);
+  msda_b200_count_launches(2);
   return int(cudaGetLastError());
 }
 
@@ -384,6 +388,7 @@ int tfb200_relu_dropout_fwd_f32(const float* a, float* h, const int64_t* seed_de
   const uint32_t thresh = t >= 4294967295.0 ? 0xffffffffu : uint32_t(t);
   relu_dropout_fwd_kernel<<<grid, 256, 0, cudaStream_t(stream)>>>(a, h, seed_dev, n4, training ? 1.f / keep_prob : 1.f,
                                                                   thresh, training);
+  msda_b200_count_launches(1);
   return int(cudaGetLastError());
 }
 
@@ -395,6 +400,7 @@ int tfb200_relu_dropout_bwd_f32(const float* grad_h, const float* h, float* grad
   const int64_t n4 = n / 4;
   const int grid = int(n4 / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
   relu_dropout_bwd_kernel<<<grid, 256, 0, cudaStream_t(stream)>>>(grad_h, h, grad_a, n4, training ? 1.f / keep_prob : 1.f);
+  msda_b200_count_launches(1);
   return int(cudaGetLastError());
 }
 
@@ -523,6 +529,7 @@ int tfb200_sampling_prep_fwd_f32(const float* proj, const float* ref, const floa
     if (LP == 4) TFB200_PREP(4, 4); else if (LP == 8) TFB200_PREP(8, 4); else if (LP == 16) TFB200_PREP(16, 4); else TFB200_PREP(32, 4);
   }
 #undef TFB200_PREP
+  msda_b200_count_launches(1);
   return int(cudaGetLastError());
 }
 
@@ -546,6 +553,7 @@ int tfb200_sampling_prep_bwd_f32(const float* grad_loc, const float* grad_attn, 
     if (LP == 4) TFB200_PREPB(4, 4); else if (LP == 8) TFB200_PREPB(8, 4); else if (LP == 16) TFB200_PREPB(16, 4); else TFB200_PREPB(32, 4);
   }
 #undef TFB200_PREPB
+  msda_b200_count_launches(1);
   return int(cudaGetLastError());
 }
 

@@ -17,6 +17,7 @@
 #include <stdint.h>
 
 #include "../../include/tfb200_fused.h"
+#include "launch_counter.h"
 
 namespace {
 
@@ -167,6 +168,7 @@ int tfb200_lsa_f32(const float* cost, const int* offsets_dev, int64_t* src, int6
     if (e != cudaSuccess) return int(e);
   }
   lsa_kernel<<<K * B, kLsaThreads, smem, cudaStream_t(stream)>>>(cost, offsets_dev, src, tgt, B, Q, T, status_dev);
+  msda_b200_count_launches(1);
   return int(cudaGetLastError());
 }
 

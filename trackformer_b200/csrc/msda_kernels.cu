@@ -24,6 +24,7 @@
 #include <atomic>
 
 #include "../../include/msda_b200.h"
+#include "launch_counter.h"
 #include "msda_common.cuh"
 #include "msda_d32.cuh"
 #include "msda_tile.cuh"
@@ -436,6 +437,7 @@ void msda_b200_set_variant(int fwd_variant, int bwd_variant) {
 }
 
 uint64_t msda_b200_launch_count(void) { return g_launches.load(); }
+void msda_b200_count_launches(int n) { g_launches.fetch_add(uint64_t(n), std::memory_order_relaxed); }
 
 int msda_b200_l1_gather_probe(const float* table, float* sink, int64_t rows, int iters, int ctas, void* stream) {
   if (!table || !sink || rows <= 0 || iters <= 0 || ctas <= 0) return MSDA_E_DIMS;

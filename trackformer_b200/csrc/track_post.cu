@@ -12,6 +12,7 @@
 #include <stdint.h>
 
 #include "../../include/tfb200_fused.h"
+#include "launch_counter.h"
 
 namespace {
 
@@ -60,5 +61,6 @@ extern "C" int tfb200_detect_postprocess_f32(const float* logits, const float* b
   const int64_t rows = int64_t(N) * Q;
   const int grid = int((rows + 7) / 8);
   detect_postprocess_kernel<<<grid, 256, 0, cudaStream_t(stream)>>>(logits, boxes, sizes_hw, packed, labels, N, Q, C);
+  msda_b200_count_launches(1);
   return int(cudaGetLastError());
 }
