@@ -39,7 +39,8 @@ def test_fixtures_exercise_every_branch():
     assert g["reid_embedding"]["num_reids"] > 0 and g["reid_greedy"]["num_reids"] > 0
     assert g["default"]["num_reids"] == 0 and len(g["default"]["inactive_ids"]) == 0
     assert g["public_center"]["track_num"] < g["default"]["track_num"]
-    assert g["public_iou"]["prev_log"].tolist()[:4] == [-1, 0, 0, 1][:4] or g["public_iou"]["prev_log"][2] == 0
+    # prev_features handed to the detector: the frame before (prev_frame_dist 1) / two frames before (2)
+    assert g["default"]["prev_log"].tolist()[:3] == [-1, 0, 1] and g["public_iou"]["prev_log"].tolist()[:4] == [-1, -1, 0, 1]
     logs = []
     scene = tf.Scene()
     det = tf.ScriptedDetector(scene)
