@@ -118,6 +118,8 @@ ORACLE_CASES = {
     "c1_encoder":   (1, 8, 32, 6380, [(60, 80), (30, 40), (15, 20), (8, 10)], 4, np.float32),
     "batch2_d32":   (2, 8, 32, 517, [(25, 42), (13, 21), (7, 11), (4, 6)], 4, np.float32),
     "d36_l8":       (1, 8, 36, 311, [(17, 30), (9, 15), (5, 8), (3, 4)] * 2, 4, np.float32),
+    "d36_heads3_thin": (2, 3, 36, 50, [(1, 7), (6, 1), (2, 2), (5, 9)], 2, np.float32),      # nine-lane kernel, M != 8
+    "d36_l4_batch2": (2, 8, 36, 1001, [(34, 60), (17, 30), (9, 15), (5, 8)], 4, np.float32),
     "d64_heads4":   (1, 4, 64, 129, [(9, 11), (5, 6)], 4, np.float32),
     "d16":          (2, 8, 16, 65, [(9, 11), (5, 6)], 4, np.float32),
     "d8_p3":        (1, 3, 8, 77, [(7, 9), (4, 5), (2, 3)], 3, np.float32),
@@ -146,6 +148,19 @@ def test_forward_backward_match_c_oracle(msda, dev, name):
     np.testing.assert_allclose(gv.cpu().numpy(), ref_gv, rtol=t["rtol"], atol=t["atol"] * scale)
     np.testing.assert_allclose(ga.cpu().numpy(), ref_ga, **t)
     np.testing.assert_allclose(gl.cpu().numpy(), ref_gl, rtol=t["rtol"] * 5, atol=t["atol"] * 50)
+
+
+def test_d36_forward_kernel_equals_generic_kernel(msda, dev):
+    """the nine-lane D = 36 forward (msda_d36.cuh) against the generic kernel (variant 1) on the same inputs"""
+    value, shapes, loc, attn, _ = rand_problem(36, 2, 8, 36, 777, [(20, 33), (10, 17), (5, 9), (3, 5)] * 2, 4, np.float32)
+    tv, ts, tl, ta = (torch.from_numpy(x).to(dev) for x in (value, shapes, loc, attn))
+    fast = msda.ms_deform_attn_forward(tv, ts, tl, ta, 64)
+    msda.set_variant(1, 0)
+    try:
+        generic = msda.ms_deform_attn_forward(tv, ts, tl, ta, 64)
+    finally:
+        msda.set_variant(0, 0)
+    torch.testing.assert_close(fast, generic, rtol=1e-5, atol=1e-6)
 
 
 def test_unaligned_views_take_the_scalar_path(msda, dev):

@@ -27,6 +27,7 @@
 #include "launch_counter.h"
 #include "msda_common.cuh"
 #include "msda_d32.cuh"
+#include "msda_d36.cuh"
 #include "msda_tile.cuh"
 
 namespace msda {
@@ -285,6 +286,24 @@ static int forward_impl(const T* value, const int64_t* shapes, const T* loc, con
 #undef MSDA_FWD_D32
       else
         msda_fwd_d32_kernel<0><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, out, d.S, d.M, d.L, d.Lq,
+                                                                d.P, uint32_t(groups), iters);
+      launched = true;
+    }
+  }
+  if constexpr (sizeof(T) == 4) {
+    // multi-frame geometry (D = 36): nine-lane groups, forward only (msda_d36.cuh); variant 1 forces the generic path
+    const int LP = d.L * d.P;
+    if (!launched && g_fwd_variant.load(std::memory_order_relaxed) != 1 && vec_ok && d.D == 36 && LP <= kMaxLP &&
+        aligned16(loc) && aligned16(attn) && groups < (int64_t(1) << 31)) {
+      const int64_t ctas = (groups + kD36GroupsPerCta - 1) / kD36GroupsPerCta;
+      const int iters = pick_iters(ctas);
+      const unsigned grid = unsigned((ctas + iters - 1) / iters);
+      const size_t smem = fwd_d36_smem_bytes(LP);
+      if (d.M == 8)
+        msda_fwd_d36_kernel<288><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, out, d.S, d.M, d.L, d.Lq,
+                                                                  d.P, uint32_t(groups), iters);
+      else
+        msda_fwd_d36_kernel<0><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, out, d.S, d.M, d.L, d.Lq,
                                                                 d.P, uint32_t(groups), iters);
       launched = true;
     }
