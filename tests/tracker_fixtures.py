@@ -245,10 +245,10 @@ def run_model_sequence(build, tracker_cls, post, cfg_overrides, size=(128, 160),
     post = _ScoreLog(post) if log_scores else post
     tracker = tracker_cls(model, {"bbox": post}, cfg, False)
     tracker.reset()
-    for frame in model_frames(size, n_frames):
-      with torch.no_grad():                     # src/track.py runs the tracker under no_grad
-        tracker.step({"img": frame[None], "orig_size": torch.tensor([[size[0] * 4, size[1] * 4]]),
-                      "dets": torch.zeros(1, 0, 4)})
+    with torch.no_grad():                         # src/track.py runs the tracker under no_grad
+        for frame in model_frames(size, n_frames):
+            tracker.step({"img": frame[None], "orig_size": torch.tensor([[size[0] * 4, size[1] * 4]]),
+                          "dets": torch.zeros(1, 0, 4)})
     out = summarise(tracker)
     if log_scores:
         out["_scores"], out["_labels"] = post.scores, post.labels
