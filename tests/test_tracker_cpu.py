@@ -153,3 +153,61 @@ def test_tracker_over_the_real_detector_matches_reference(name, multi_frame, mon
     assert out["rows"].shape == gold["rows"].shape
     np.testing.assert_array_equal(out["rows"][:, :3], gold["rows"][:, :3])
     np.testing.assert_allclose(out["rows"][:, 3:], gold["rows"][:, 3:], rtol=1e-3, atol=1e-3)
+
+
+class _Silent(torch.nn.Module):
+    """detector that never scores above any threshold"""
+    num_queries, overflow_boxes, hidden_dim = 10, False, 8
+
+    def __init__(self):
+        super().__init__()
+        self.p = torch.nn.Parameter(torch.zeros(1))
+        self.calls = []
+
+    def forward(self, img, targets=None, prev_features=None):
+        self.calls.append(None if targets is None else len(targets[0]["track_query_boxes"]))
+        q = self.num_queries + (self.calls[-1] or 0)
+        out = {"pred_logits": torch.full((1, q, 3), -6.0), "pred_boxes": torch.full((1, q, 4), 0.5),
+               "hs_embed": torch.zeros(1, q, self.hidden_dim)}
+        return out, None, None, None, None
+
+
+def test_no_detections_means_no_tracks_and_no_track_queries():
+    det = _Silent()
+    tr = Tracker(det, {"bbox": DeformablePostProcess()}, tf.tracker_cfg("reid_embedding"), False)
+    for _ in range(3):
+        tr.step({"img": torch.zeros(1, 3, 8, 8), "orig_size": torch.tensor([[100, 200]])})      # no 'dets' key either
+    assert tr.results == {} and tr.tracks == [] and tr.inactive_tracks == [] and tr.track_num == 0
+    assert det.calls == [None, None, None] and tr.frame_index == 3
+
+
+def test_boxes_are_clipped_to_the_image_unless_overflow_is_allowed():
+    class Edge(_Silent):
+        def forward(self, img, targets=None, prev_features=None):
+            out, *rest = super().forward(img, targets, prev_features)
+            k = out["pred_logits"].shape[1] - self.num_queries
+            out["pred_logits"][0, k, 0] = 3.0                       # one confident person ...
+            out["pred_boxes"][0, k] = torch.tensor([0.98, 0.5, 0.2, 0.4])      # ... sticking out on the right
+            return (out, *rest)
+    for overflow, x1 in ((False, 200.0), (True, 216.0)):
+        det = Edge()
+        det.overflow_boxes = overflow
+        tr = Tracker(det, {"bbox": DeformablePostProcess()}, tf.tracker_cfg("default"), False)
+        tr.step({"img": torch.zeros(1, 3, 8, 8), "orig_size": torch.tensor([[100, 200]]), "dets": torch.zeros(1, 0, 4)})
+        (res,) = tr.results[0].values()
+        np.testing.assert_allclose(res["bbox"], [176.0, 30.0, x1, 70.0], rtol=1e-6)
+        assert res["obj_ind"] == 0 and res["score"].shape == () and res["score"].dtype == np.float32
+
+
+def test_generic_postprocessor_route_equals_packed_route():
+    """a reference-shaped post-processor (no `packed`) gives the tracker the same rows"""
+    class Plain:
+        def __init__(self):
+            self.inner = DeformablePostProcess()
+
+        def __call__(self, outputs, sizes):
+            return self.inner(outputs, sizes)
+    a = tf.run_case(Tracker, DeformablePostProcess(), "reid_greedy")
+    b = tf.run_case(Tracker, Plain(), "reid_greedy")
+    for key in a:
+        np.testing.assert_array_equal(a[key], b[key], err_msg=key)
