@@ -133,3 +133,46 @@ def test_msdeformattn_init_constants_match_reference_recipe():
               m.output_proj.bias):
         assert not t.detach().any()
     assert m.value_proj.weight.detach().abs().max() > 0 and m.output_proj.weight.detach().abs().max() > 0
+
+
+def test_frozen_batchnorm_affine_cache_tracks_its_buffers():
+    """the cached (scale, shift) pair equals a fresh computation and is dropped when a buffer is written or copied"""
+    import copy
+    from trackformer_b200.backbone import FrozenBatchNorm2d
+    bn = FrozenBatchNorm2d(6)
+    g = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(6, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(6, generator=g))
+        bn.running_mean.copy_(torch.randn(6, generator=g))
+        bn.running_var.copy_(torch.rand(6, generator=g) + 0.1)
+    x = torch.randn(2, 6, 5, 7, generator=g, requires_grad=True)
+
+    def fresh(m, t):
+        w, b, rm, rv = (v.view(1, -1, 1, 1) for v in (m.weight, m.bias, m.running_mean, m.running_var))
+        scale = w * (rv + 1e-5).rsqrt()
+        return t * scale + (b - rm * scale)
+    y1 = bn(x)
+    torch.testing.assert_close(y1, fresh(bn, x), rtol=1e-6, atol=1e-6)
+    s1 = bn.affine()[0]
+    assert bn.affine()[0] is s1                                   # reused
+    y1.sum().backward()                                           # the cached pair works inside autograd
+    assert x.grad is not None
+    with torch.no_grad():
+        bn.running_var.mul_(2.0)                                  # in-place write -> recomputed
+    assert bn.affine()[0] is not s1
+    torch.testing.assert_close(bn(x), fresh(bn, x), rtol=1e-6, atol=1e-6)
+    clone = copy.deepcopy(bn)
+    with torch.no_grad():
+        clone.bias.add_(1.0)
+    torch.testing.assert_close(clone(x), fresh(clone, x), rtol=1e-6, atol=1e-6)
+    bn.load_state_dict({k: torch.ones(6) for k in ("weight", "bias", "running_mean", "running_var")})
+    torch.testing.assert_close(bn(x), fresh(bn, x), rtol=1e-6, atol=1e-6)
+    bn2 = FrozenBatchNorm2d(6)
+    with torch.inference_mode():
+        bn2(torch.zeros(1, 6, 2, 2))
+    assert getattr(bn2, "_affine_cache", None) is None           # nothing cached under inference mode
+    bn2(x).sum().backward()
+    with torch.inference_mode():
+        bn3 = FrozenBatchNorm2d(6)                               # buffers that ARE inference tensors
+    assert bn3(torch.zeros(1, 6, 2, 2)).shape == (1, 6, 2, 2) and getattr(bn3, "_affine_cache", None) is None
