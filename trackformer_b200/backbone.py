@@ -62,7 +62,22 @@ class FrozenBatchNorm2d(nn.Module):
         return torch.addcmul(shift, x, scale)             # one pass: x * scale + shift
 
 
+_DENSE_MASKS: Dict[tuple, torch.Tensor] = {}
+
+
 def _resize_mask(mask: torch.Tensor, size) -> torch.Tensor:
+    """Nearest-neighbour resize of the padding mask to a feature map's size (backbone.py:80-88).  For a batch known to
+    be dense (`_no_padding`) the result is all False whatever the size: one shared tensor per (batch, size, device)
+    instead of three small launches per level and frame."""
+    size = tuple(int(v) for v in size)
+    if getattr(mask, "_no_padding", False) and not torch.is_inference_mode_enabled():
+        key = (int(mask.shape[0]), size, mask.device)
+        hit = _DENSE_MASKS.get(key)
+        if hit is None:
+            hit = torch.zeros((mask.shape[0],) + size, dtype=torch.bool, device=mask.device)
+            hit._no_padding = True
+            _DENSE_MASKS[key] = hit
+        return hit
     out = F.interpolate(mask[None].float(), size=size).to(torch.bool)[0]
     if getattr(mask, "_no_padding", False):
         out._no_padding = True

@@ -15,6 +15,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from .backbone import _resize_mask
 from .util import (NestedTensor, box_cxcywh_to_xyxy, inverse_sigmoid,
                    nested_tensor_from_tensor_list)
 
@@ -149,10 +150,7 @@ class DeformableDETR(DETR):
                     src = self.input_proj[l](frame_feat[-1].tensors)
             else:
                 src = self.input_proj[l](src_list[-1])
-            m0 = frame_feat[0].mask
-            mask = F.interpolate(m0[None].float(), size=src.shape[-2:]).to(torch.bool)[0]
-            if getattr(m0, "_no_padding", False):
-                mask._no_padding = True
+            mask = _resize_mask(frame_feat[0].mask, src.shape[-2:])
             pos_l = self.backbone[1](NestedTensor(src, mask)).to(src.dtype)
             src_list.append(src)
             mask_list.append(mask)

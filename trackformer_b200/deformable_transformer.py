@@ -245,22 +245,33 @@ class DeformableTransformer(nn.Module):
         vw = (~mask[:, 0, :]).sum(1).float() / w
         return torch.stack([vw, vh], -1)
 
+    def _unit_ratios(self, batch, levels, device):
+        key = (batch, levels, device)
+        memo = self.__dict__.setdefault("_unit_ratio_memo", {})
+        hit = memo.get(key)
+        if hit is None or torch.is_inference_mode_enabled():
+            hit = torch.ones(batch, levels, 2, dtype=torch.float32, device=device)
+            if not torch.is_inference_mode_enabled():
+                memo[key] = hit
+        return hit
+
     def forward(self, srcs, masks, pos_embeds, query_embed=None, targets=None):
         assert query_embed is not None
-        hw, src_l, mask_l, pos_l = [], [], [], []
-        for lvl, (src, mask, pos) in enumerate(zip(srcs, masks, pos_embeds)):
+        hw, src_l, pos_l = [], [], []
+        for lvl, (src, pos) in enumerate(zip(srcs, pos_embeds)):
             hw.append((int(src.shape[2]), int(src.shape[3])))
             src_l.append(src.flatten(2).transpose(1, 2))
-            mask_l.append(mask.flatten(1))
             pos_l.append(pos.flatten(2).transpose(1, 2) + self.level_embed[lvl].view(1, 1, -1))
         src_flat = torch.cat(src_l, 1)
-        mask_flat = torch.cat(mask_l, 1)
         pos_flat = torch.cat(pos_l, 1)
         spatial_shapes = self._shapes_tensor(hw, src_flat.device)
-        valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
         dense = all(getattr(m, "_no_padding", False) for m in masks)
-        enc_mask = None if dense else mask_flat          # an all-False mask is a no-op in MSDeformAttn
-
+        if dense:                                        # no padding anywhere: unit valid ratios, and an all-False
+            enc_mask = None                              # mask is a no-op in MSDeformAttn -> nothing to build
+            valid_ratios = self._unit_ratios(src_flat.shape[0], len(masks), src_flat.device)
+        else:
+            enc_mask = torch.cat([m.flatten(1) for m in masks], 1)
+            valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
         if self.multi_frame_attention_separate_encoder:
             half_s, half_l = src_flat.shape[1] // 2, self.num_feature_levels // 2
 
