@@ -38,3 +38,29 @@ def test_flat_layout_keeps_the_model_and_partitions_groups(oracle_op):
         step.flat_optimizer.step()                       # CUDA-only update: no CPU fallback
     with pytest.raises(AssertionError):
         TrainStep(model, criterion, None, use_graphs=False, flat_adamw={"groups": groups[:2]})
+
+
+def test_detector_core_returns_the_stacked_heads(oracle_op):
+    """_DetectorCore hands out the per-layer heads the model stacked itself; values and gradients equal re-stacking the
+    slices of the output dictionary"""
+    from trackformer_b200.train_step import _DetectorCore
+    model, _ = build(False, False, enc_layers=1, dec_layers=3, num_queries=20, dropout=0.0)
+    mf.canonical_weights_(model, 0)
+    model.train()
+    core = _DetectorCore(model)
+    x = mf.make_images(3, [(96, 128)])[0][None]
+    logits, boxes = core(x)
+    assert logits.shape[0] == boxes.shape[0] == 3 and model._stacked_heads[0] is logits
+    out = model(x, None, None)[0]
+    re_logits = torch.stack([a["pred_logits"] for a in out["aux_outputs"]] + [out["pred_logits"]])
+    re_boxes = torch.stack([a["pred_boxes"] for a in out["aux_outputs"]] + [out["pred_boxes"]])
+    torch.testing.assert_close(logits, re_logits, rtol=0, atol=0)
+    torch.testing.assert_close(boxes, re_boxes, rtol=0, atol=0)
+    params = [p for p in model.parameters() if p.requires_grad]
+    w = torch.randn(logits.shape, generator=torch.Generator().manual_seed(0))
+    ga = torch.autograd.grad((logits * w).sum() + boxes.sum(), params, allow_unused=True)
+    gb = torch.autograd.grad((re_logits * w).sum() + re_boxes.sum(), params, allow_unused=True)
+    for a, b in zip(ga, gb):
+        assert (a is None) == (b is None)
+        if a is not None:
+            torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6 * max(1.0, float(b.abs().max())))

@@ -157,6 +157,7 @@ class DeformableDETR(DETR):
             pos_list.append(pos_l[:, frame] if use_3d else pos_l)
 
     def forward(self, samples: NestedTensor, targets: list = None, prev_features=None):
+        self._stacked_heads = None                       # do not keep the previous call's graph alive
         if not isinstance(samples, NestedTensor):
             samples = nested_tensor_from_tensor_list(samples)
         features_all, pos = self.backbone(samples)
@@ -184,6 +185,9 @@ class DeformableDETR(DETR):
             boxes.append(delta.sigmoid())
         logits = torch.stack(logits)
         boxes = torch.stack(boxes)
+        # per-layer heads as two tensors [layers, N, Q, .]; the training step takes them from here instead of
+        # re-stacking the per-layer slices of the output dictionary (whose backward is a zero-fill + copy per slice)
+        self._stacked_heads = (logits, boxes)
 
         out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1], "hs_embed": hs[-1]}
         if self.aux_loss:
