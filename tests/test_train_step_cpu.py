@@ -50,7 +50,10 @@ def test_detector_core_returns_the_stacked_heads(oracle_op):
     core = _DetectorCore(model)
     x = mf.make_images(3, [(96, 128)])[0][None]
     logits, boxes = core(x)
-    assert logits.shape[0] == boxes.shape[0] == 3 and model._stacked_heads[0] is logits
+    assert logits.shape[0] == boxes.shape[0] == 3 and model.stacked_heads[0] is logits
+    import copy
+    clone = copy.deepcopy(model)                         # still deep-copyable after a training forward
+    assert clone.stacked_heads is None and len(clone.state_dict()) == len(model.state_dict())
     out = model(x, None, None)[0]
     re_logits = torch.stack([a["pred_logits"] for a in out["aux_outputs"]] + [out["pred_logits"]])
     re_boxes = torch.stack([a["pred_boxes"] for a in out["aux_outputs"]] + [out["pred_boxes"]])

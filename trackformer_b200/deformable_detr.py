@@ -69,6 +69,21 @@ class DETR(nn.Module):
         return [{"pred_logits": a, "pred_boxes": b} for a, b in zip(outputs_class[:-1], outputs_coord[:-1])]
 
 
+class _CallScratch:
+    """Holder for tensors of the latest forward call (they carry autograd history): kept out of copies and pickles of
+    the module, which must stay deep-copyable after a training forward."""
+    __slots__ = ("value",)
+
+    def __init__(self):
+        self.value = None
+
+    def __deepcopy__(self, memo):
+        return _CallScratch()
+
+    def __reduce__(self):
+        return (_CallScratch, ())
+
+
 class DeformableDETR(DETR):
     def __init__(self, backbone, transformer, num_classes, num_queries, num_feature_levels, aux_loss=True,
                  with_box_refine=False, two_stage=False, overflow_boxes=False, multi_frame_attention=False,
@@ -156,8 +171,19 @@ class DeformableDETR(DETR):
             mask_list.append(mask)
             pos_list.append(pos_l[:, frame] if use_3d else pos_l)
 
+    def _call_scratch(self) -> _CallScratch:
+        holder = self.__dict__.get("_scratch")
+        if holder is None:
+            holder = self.__dict__["_scratch"] = _CallScratch()
+        return holder
+
+    @property
+    def stacked_heads(self):
+        """(logits [layers, N, Q, classes], boxes [layers, N, Q, 4]) of the latest forward call, or None"""
+        return self._call_scratch().value
+
     def forward(self, samples: NestedTensor, targets: list = None, prev_features=None):
-        self._stacked_heads = None                       # do not keep the previous call's graph alive
+        self._call_scratch().value = None                # do not keep the previous call's graph alive
         if not isinstance(samples, NestedTensor):
             samples = nested_tensor_from_tensor_list(samples)
         features_all, pos = self.backbone(samples)
@@ -187,7 +213,7 @@ class DeformableDETR(DETR):
         boxes = torch.stack(boxes)
         # per-layer heads as two tensors [layers, N, Q, .]; the training step takes them from here instead of
         # re-stacking the per-layer slices of the output dictionary (whose backward is a zero-fill + copy per slice)
-        self._stacked_heads = (logits, boxes)
+        self._call_scratch().value = (logits, boxes)
 
         out = {"pred_logits": logits[-1], "pred_boxes": boxes[-1], "hs_embed": hs[-1]}
         if self.aux_loss:

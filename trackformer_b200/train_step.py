@@ -37,9 +37,8 @@ class _DetectorCore(nn.Module):
         self.model = model
 
     def forward(self, frames):
-        self.model._stacked_heads = None
         out, _, _, _, _ = self.model(frames, None, None)
-        stacked = getattr(self.model, "_stacked_heads", None)
+        stacked = getattr(self.model, "stacked_heads", None)
         if stacked is not None and stacked[0].shape[0] == len(out["aux_outputs"]) + 1:
             return stacked                           # the very tensors the dictionary entries are slices of
         logits = torch.stack([a["pred_logits"] for a in out["aux_outputs"]] + [out["pred_logits"]])
