@@ -87,6 +87,15 @@ int tfb200_flat_adamw_f32(float* param, const float* grad, float* exp_avg, float
                           const float* grad_norm_dev, float max_norm, float lr, float beta1, float beta2, float eps,
                           float weight_decay, int64_t step, void* stream);
 
+/* Frozen batch-norm + optional residual add + optional ReLU over channels-last activations ([pixels][C], C % 4 == 0):
+ *   y = act(x * scale[c] + shift[c] (+ residual))          backbone.py:46-55 + torchvision Bottleneck.forward
+ * backward: g = relu ? dy * (y > 0) : dy;  dx = g * scale[c] (NULL to skip);  dresidual = g (NULL when there was no
+ * residual).  scale / shift are the folded per-channel terms (weight * rsqrt(var + eps), bias - mean * scale).        */
+int tfb200_frozen_bn_act_fwd_f32(const float* x, const float* residual, const float* scale, const float* shift,
+                                 float* y, int64_t pixels, int C, int relu, void* stream);
+int tfb200_frozen_bn_act_bwd_f32(const float* dy, const float* y, const float* scale, float* dx, float* dresidual,
+                                 int64_t pixels, int C, int relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
