@@ -39,6 +39,18 @@ int tfb200_add_dropout_layernorm_bwd_f32(const float* dy, const float* s, const 
                                          float* dbranch, float* dgamma, float* dbeta, float* partial_ws,
                                          int64_t rows, int C, float keep_prob, void* stream);
 
+/* Same pair with mask-free dropout: keep decisions are a counter-based hash of (*seed_dev, element index) against
+ * keep_prob (the scheme of tfb200_relu_dropout_*), so no mask tensor is drawn, stored or read; forward and backward
+ * must be given the same seed.                                                                                        */
+int tfb200_add_dropout_layernorm_seeded_fwd_f32(const float* x, const float* branch, const int64_t* seed_dev,
+                                                const float* gamma, const float* beta, float* s_out, float* y,
+                                                float* mean, float* rstd, int64_t rows, int C, float keep_prob,
+                                                float eps, void* stream);
+int tfb200_add_dropout_layernorm_seeded_bwd_f32(const float* dy, const float* s, const int64_t* seed_dev,
+                                                const float* gamma, const float* mean, const float* rstd, float* dx,
+                                                float* dbranch, float* dgamma, float* dbeta, float* partial_ws,
+                                                int64_t rows, int C, float keep_prob, void* stream);
+
 /* out[c] = sum_r x[r][c]  (bias gradient of a Linear over a long token axis); C % 4 == 0, C <= 1024;
  * partial_ws: [tfb200_ln_partial_ctas(rows)][C] fp32.  Deterministic (fixed summation order).                      */
 int tfb200_colsum_f32(const float* x, float* out, float* partial_ws, int64_t rows, int C, void* stream);
