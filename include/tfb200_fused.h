@@ -39,6 +39,18 @@ int tfb200_add_dropout_layernorm_bwd_f32(const float* dy, const float* s, const 
                                          float* dbranch, float* dgamma, float* dbeta, float* partial_ws,
                                          int64_t rows, int C, float keep_prob, void* stream);
 
+/* Same pair with mask-free dropout: keep decisions are a counter-based hash of (*seed_dev, element index) against
+ * keep_prob (the scheme of tfb200_relu_dropout_*), so no mask tensor is drawn, stored or read; forward and backward
+ * must be given the same seed.                                                                                        */
+int tfb200_add_dropout_layernorm_seeded_fwd_f32(const float* x, const float* branch, const int64_t* seed_dev,
+                                                const float* gamma, const float* beta, float* s_out, float* y,
+                                                float* mean, float* rstd, int64_t rows, int C, float keep_prob,
+                                                float eps, void* stream);
+int tfb200_add_dropout_layernorm_seeded_bwd_f32(const float* dy, const float* s, const int64_t* seed_dev,
+                                                const float* gamma, const float* mean, const float* rstd, float* dx,
+                                                float* dbranch, float* dgamma, float* dbeta, float* partial_ws,
+                                                int64_t rows, int C, float keep_prob, void* stream);
+
 /* out[c] = sum_r x[r][c]  (bias gradient of a Linear over a long token axis); C % 4 == 0, C <= 1024;
  * partial_ws: [tfb200_ln_partial_ctas(rows)][C] fp32.  Deterministic (fixed summation order).                      */
 int tfb200_colsum_f32(const float* x, float* out, float* partial_ws, int64_t rows, int C, void* stream);
@@ -86,6 +98,15 @@ int tfb200_detect_postprocess_f32(const float* logits, const float* boxes, const
 int tfb200_flat_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                           const float* grad_norm_dev, float max_norm, float lr, float beta1, float beta2, float eps,
                           float weight_decay, int64_t step, void* stream);
+
+/* Frozen batch-norm + optional residual add + optional ReLU over channels-last activations ([pixels][C], C % 4 == 0):
+ *   y = act(x * scale[c] + shift[c] (+ residual))          backbone.py:46-55 + torchvision Bottleneck.forward
+ * backward: g = relu ? dy * (y > 0) : dy;  dx = g * scale[c] (NULL to skip);  dresidual = g (NULL when there was no
+ * residual).  scale / shift are the folded per-channel terms (weight * rsqrt(var + eps), bias - mean * scale).        */
+int tfb200_frozen_bn_act_fwd_f32(const float* x, const float* residual, const float* scale, const float* shift,
+                                 float* y, int64_t pixels, int C, int relu, void* stream);
+int tfb200_frozen_bn_act_bwd_f32(const float* dy, const float* y, const float* scale, float* dx, float* dresidual,
+                                 int64_t pixels, int C, int relu, void* stream);
 
 #ifdef __cplusplus
 }

@@ -155,3 +155,40 @@ def test_sampling_prep_matches_torch_chain(dev, ref_dim, L, P, Lq):
     (g1,) = torch.autograd.grad([loc, attn], [proj], [gl, ga])
     (g2,) = torch.autograd.grad([l_ref, a_ref], [p2], [gl, ga])
     torch.testing.assert_close(g1, g2, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("rows,C,p", [(22223, 256, 0.1), (4097, 288, 0.3), (33, 128, 0.5)])
+def test_seeded_dropout_layernorm(dev, rows, C, p):
+    """mask-free dropout inside the fused residual+LayerNorm: the kept set is reproducible from the seed, has the right
+    rate, and forward / backward agree with the torch chain run on the SAME kept set"""
+    from trackformer_b200 import ext
+    m = ext.load()
+    g = torch.Generator().manual_seed(rows + C)
+    x = torch.randn(rows, C, generator=g).to(dev)
+    br = torch.randn(rows, C, generator=g).to(dev)
+    gamma = (torch.rand(C, generator=g) + 0.5).to(dev)
+    beta = torch.randn(C, generator=g).to(dev)
+    dy = torch.randn(rows, C, generator=g).to(dev)
+    seed = torch.tensor([123456789012345], dtype=torch.int64, device=dev)
+    keep = 1.0 - p
+    y, s, mean, rstd = m.add_dropout_layernorm_seeded_forward(x, br, seed, gamma, beta, keep, 1e-5)
+    # recover the kept set from s = x + branch * kept / keep
+    kept = ((s - x).abs() > 0) | (br == 0)
+    rate = float(kept.float().mean())
+    assert abs(rate - keep) < 4 * (keep * p / kept.numel()) ** 0.5 + 1e-3
+    xr, brr = x.clone().requires_grad_(True), br.clone().requires_grad_(True)
+    gr, btr = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    s_ref = xr + brr * kept / keep
+    y_ref = torch.nn.functional.layer_norm(s_ref, (C,), gr, btr, 1e-5)
+    torch.testing.assert_close(y, y_ref, rtol=1e-4, atol=1e-4)
+    y_ref.backward(dy)
+    dx, dbr, dgamma, dbeta = m.add_dropout_layernorm_seeded_backward(dy, s, seed, gamma, mean, rstd, keep)
+    torch.testing.assert_close(dx, xr.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dbr, brr.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dgamma, gr.grad, rtol=1e-3, atol=1e-3 * float(gr.grad.abs().max()))
+    torch.testing.assert_close(dbeta, btr.grad, rtol=1e-3, atol=1e-3 * float(btr.grad.abs().max()))
+    # same seed -> same kept set; another seed -> another one
+    y2 = m.add_dropout_layernorm_seeded_forward(x, br, seed, gamma, beta, keep, 1e-5)[0]
+    assert torch.equal(y, y2)
+    y3 = m.add_dropout_layernorm_seeded_forward(x, br, seed + 1, gamma, beta, keep, 1e-5)[0]
+    assert not torch.equal(y, y3)

@@ -67,3 +67,30 @@ def test_detector_core_returns_the_stacked_heads(oracle_op):
         assert (a is None) == (b is None)
         if a is not None:
             torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6 * max(1.0, float(b.abs().max())))
+
+
+def test_gradient_handover_equals_accumulation(oracle_op):
+    """_backward_into_flat: gathering the handed-over gradients gives the flat buffer the accumulating path gives,
+    including a zeroed slice for a parameter that received no gradient"""
+    import copy
+    from trackformer_b200.train_step import TrainStep
+    model, criterion = build(False, False, enc_layers=1, dec_layers=2, num_queries=20, dropout=0.0)
+    mf.canonical_weights_(model, 0)
+    model.train()
+    model_b = copy.deepcopy(model)
+    x = mf.make_images(3, [(96, 128)])[0][None]
+    targets = mf.make_targets(4, 1, 3)
+    gather = TrainStep(model, criterion, None, use_graphs=False)
+    accumulate = TrainStep(model_b, criterion, None, use_graphs=False)
+    gather.gather_grads, accumulate.gather_grads = True, False
+    gather.flat_grad.fill_(7.0)                          # stale content must not survive either path
+    accumulate.flat_grad.fill_(7.0)
+    la, lb = gather(x, targets), accumulate(x, targets)
+    torch.testing.assert_close(la, lb, rtol=0, atol=0)
+    pads = torch.ones_like(gather.flat_grad, dtype=torch.bool)
+    for p in gather.params:
+        o = (p.grad.data_ptr() - gather.flat_grad.data_ptr()) // 4
+        pads[o:o + p.numel()] = False
+        assert p.grad.data_ptr() >= gather.flat_grad.data_ptr()          # the flat views are back in place
+    torch.testing.assert_close(gather.flat_grad[~pads], accumulate.flat_grad[~pads], rtol=0, atol=0)
+    assert float(gather.flat_grad[~pads].abs().sum()) > 0

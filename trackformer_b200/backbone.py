@@ -97,7 +97,14 @@ class _Trunk(nn.ModuleDict):
 
     def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
         collected = {}
+        fuse_stem = getattr(self, "fused_bn", False)
         for name, stage in self.items():
+            if fuse_stem and name == "bn1":
+                from .fused_bn import bn_act
+                x = bn_act(x, stage, True)             # stem: bn1 + relu in one pass
+                continue
+            if fuse_stem and name == "relu":
+                continue
             x = stage(x)
             key = self.taps.get(name)
             if key is not None:
@@ -128,6 +135,7 @@ class BackboneBase(nn.Module):
         # [N, C, H, W] -> [N, H*W, C] flatten the transformer needs becomes a view.  Values are unchanged.
         # (applied on first CUDA use; CPU runs -- tests, the CPU baseline -- keep the reference's NCHW execution.)
         self.channels_last = os.environ.get("TFB200_CHANNELS_LAST", "1") != "0"
+        self.fused_bn = os.environ.get("TFB200_FUSED_BN", "1") != "0"
         self._filters_nhwc = False
 
     def prepare(self) -> None:
@@ -136,6 +144,9 @@ class BackboneBase(nn.Module):
         if self.channels_last and not self._filters_nhwc and next(self.body.parameters()).is_cuda:
             self.body.to(memory_format=torch.channels_last)
             self._filters_nhwc = True
+            if self.fused_bn:                           # NHWC activations from here on: fused FrozenBN + ReLU kernels
+                from .fused_bn import patch_trunk
+                self.body.fused_bn = patch_trunk(self.body) > 0
 
     def forward(self, tensor_list: NestedTensor) -> Dict[str, NestedTensor]:
         frames, pad = tensor_list.tensors, tensor_list.mask

@@ -33,6 +33,16 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Counter-based keep decision for mask-free inverted dropout: a hash of (seed, element index) against a threshold.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool keep_elem(uint64_t seed, uint64_t idx, uint32_t keep_thresh) {
+  const uint32_t h = mix32(uint32_t(idx) ^ mix32(uint32_t(idx >> 32) + uint32_t(seed)) ^ uint32_t(seed >> 32) * 0x9e3779b9u);
+  return h < keep_thresh;
+}
+
 // PACKS = ceil(C / 128): a lane owns float4 packs lane, lane + 32, ...; packs beyond C/4 are masked, so any C % 4 == 0
 // up to PACKS * 128 works (256 for the shipped models, 288 for the multi-frame TrackFormer configuration).
 template <int PACKS>
@@ -41,7 +51,8 @@ add_dropout_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__
                           const uint8_t* __restrict__ mask, const float* __restrict__ gamma,
                           const float* __restrict__ beta, float* __restrict__ s_out, float* __restrict__ y,
                           float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int C, float inv_keep,
-                          float eps) {
+                          float eps, const int64_t* __restrict__ seed_ptr, uint32_t keep_thresh) {
+  const uint64_t seed = seed_ptr != nullptr ? uint64_t(__ldg(seed_ptr)) : 0;
   const int npk = C >> 2;
   const float inv_c = 1.f / float(C);
   const int lane = threadIdx.x & 31;
@@ -72,6 +83,12 @@ add_dropout_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__
           b.y = m.y ? b.y * inv_keep : 0.f;
           b.z = m.z ? b.z * inv_keep : 0.f;
           b.w = m.w ? b.w * inv_keep : 0.f;
+        } else if (seed_ptr != nullptr) {
+          const uint64_t e = uint64_t(r) * C + 4 * (k * 32 + lane);
+          b.x = keep_elem(seed, e + 0, keep_thresh) ? b.x * inv_keep : 0.f;
+          b.y = keep_elem(seed, e + 1, keep_thresh) ? b.y * inv_keep : 0.f;
+          b.z = keep_elem(seed, e + 2, keep_thresh) ? b.z * inv_keep : 0.f;
+          b.w = keep_elem(seed, e + 3, keep_thresh) ? b.w * inv_keep : 0.f;
         }
         s[k] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
         sum += (s[k].x + s[k].y) + (s[k].z + s[k].w);
@@ -112,7 +129,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s, const uint8_t* __restrict__ mask,
                           const float* __restrict__ gamma, const float* __restrict__ mean_in,
                           const float* __restrict__ rstd_in, float* __restrict__ dx, float* __restrict__ dbranch,
-                          float* __restrict__ partial, int64_t rows, int C, float inv_keep) {
+                          float* __restrict__ partial, int64_t rows, int C, float inv_keep,
+                          const int64_t* __restrict__ seed_ptr, uint32_t keep_thresh) {
+  const uint64_t seed = seed_ptr != nullptr ? uint64_t(__ldg(seed_ptr)) : 0;
   constexpr int CP = PACKS * 128;                  // padded width of the shared reduction buffer
   __shared__ float red[kWarpsPerCta][2][CP];
   const int npk = C >> 2;
@@ -166,6 +185,12 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict_
             ds.y = m.y ? ds.y * inv_keep : 0.f;
             ds.z = m.z ? ds.z * inv_keep : 0.f;
             ds.w = m.w ? ds.w * inv_keep : 0.f;
+          } else if (seed_ptr != nullptr) {
+            const uint64_t e = uint64_t(r) * C + 4 * (k * 32 + lane);
+            ds.x = keep_elem(seed, e + 0, keep_thresh) ? ds.x * inv_keep : 0.f;
+            ds.y = keep_elem(seed, e + 1, keep_thresh) ? ds.y * inv_keep : 0.f;
+            ds.z = keep_elem(seed, e + 2, keep_thresh) ? ds.z * inv_keep : 0.f;
+            ds.w = keep_elem(seed, e + 3, keep_thresh) ? ds.w * inv_keep : 0.f;
           }
           reinterpret_cast<float4*>(dbranch + r * C)[k * 32 + lane] = ds;
         }
@@ -246,14 +271,6 @@ colsum_kernel(const float* __restrict__ x, float* __restrict__ partial, int64_t 
 
 // Fused ReLU + inverted dropout for the FFN hidden activation, mask-free: the keep decision is a counter-based hash
 // of (seed, element index); the backward needs no mask because h > 0 <=> (a > 0 and kept).
-__device__ __forceinline__ uint32_t mix32(uint32_t x) {
-  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
-  return x;
-}
-__device__ __forceinline__ bool keep_elem(uint64_t seed, uint64_t idx, uint32_t keep_thresh) {
-  const uint32_t h = mix32(uint32_t(idx) ^ mix32(uint32_t(idx >> 32) + uint32_t(seed)) ^ uint32_t(seed >> 32) * 0x9e3779b9u);
-  return h < keep_thresh;
-}
 
 __global__ void __launch_bounds__(256)
 relu_dropout_fwd_kernel(const float* __restrict__ a, float* __restrict__ h, const int64_t* __restrict__ seed_ptr,
@@ -297,19 +314,24 @@ extern "C" {
 
 int tfb200_ln_partial_ctas(int64_t rows) { return grid_for(rows); }
 
-int tfb200_add_dropout_layernorm_fwd_f32(const float* x, const float* branch, const uint8_t* keep_mask,
-                                         const float* gamma, const float* beta, float* s_out, float* y,
-                                         float* mean, float* rstd, int64_t rows, int C, float keep_prob, float eps,
-                                         void* stream) {
+static uint32_t keep_threshold(float keep_prob) {
+  const double t = double(keep_prob) * 4294967296.0;
+  return t >= 4294967295.0 ? 0xffffffffu : uint32_t(t);
+}
+
+static int ln_forward(const float* x, const float* branch, const uint8_t* keep_mask, const int64_t* seed_dev,
+                      const float* gamma, const float* beta, float* s_out, float* y, float* mean, float* rstd,
+                      int64_t rows, int C, float keep_prob, float eps, void* stream) {
   if (!x || !branch || !gamma || !beta || !y) return TFB200_E_NULLPTR;
   if (rows < 0 || C <= 0 || C % 4 != 0 || C > 128 * kMaxPacks) return TFB200_E_SHAPE;
   if (rows == 0) return 0;
-  const float inv_keep = keep_mask ? 1.f / keep_prob : 1.f;
+  const float inv_keep = (keep_mask || seed_dev) ? 1.f / keep_prob : 1.f;
+  const uint32_t thresh = keep_threshold(keep_prob);
   const int grid = grid_for(rows);
   cudaStream_t st = cudaStream_t(stream);
 #define TFB200_FWD(P)                                                                                          \
   add_dropout_ln_fwd_kernel<P><<<grid, kWarpsPerCta * 32, 0, st>>>(x, branch, keep_mask, gamma, beta, s_out, y, \
-                                                                   mean, rstd, rows, C, inv_keep, eps)
+                                                                   mean, rstd, rows, C, inv_keep, eps, seed_dev, thresh)
   switch ((C + 127) / 128) {
     case 1: TFB200_FWD(1); break;
     case 2: TFB200_FWD(2); break;
@@ -323,10 +345,10 @@ int tfb200_add_dropout_layernorm_fwd_f32(const float* x, const float* branch, co
   return int(cudaGetLastError());
 }
 
-int tfb200_add_dropout_layernorm_bwd_f32(const float* dy, const float* s, const uint8_t* keep_mask,
-                                         const float* gamma, const float* mean, const float* rstd, float* dx,
-                                         float* dbranch, float* dgamma, float* dbeta, float* partial_ws,
-                                         int64_t rows, int C, float keep_prob, void* stream) {
+static int ln_backward(const float* dy, const float* s, const uint8_t* keep_mask, const int64_t* seed_dev,
+                       const float* gamma, const float* mean, const float* rstd, float* dx, float* dbranch,
+                       float* dgamma, float* dbeta, float* partial_ws, int64_t rows, int C, float keep_prob,
+                       void* stream) {
   if (!dy || !s || !gamma || !mean || !rstd || !dx || !dgamma || !dbeta || !partial_ws) return TFB200_E_NULLPTR;
   if (rows < 0 || C <= 0 || C % 4 != 0 || C > 512) return TFB200_E_SHAPE;
   cudaStream_t st = cudaStream_t(stream);
@@ -335,11 +357,12 @@ int tfb200_add_dropout_layernorm_bwd_f32(const float* dy, const float* s, const 
     cudaMemsetAsync(dbeta, 0, sizeof(float) * C, st);
     return int(cudaGetLastError());
   }
-  const float inv_keep = keep_mask ? 1.f / keep_prob : 1.f;
+  const float inv_keep = (keep_mask || seed_dev) ? 1.f / keep_prob : 1.f;
+  const uint32_t thresh = keep_threshold(keep_prob);
   const int grid = grid_for(rows);
 #define TFB200_BWD(P)                                                                                           \
   add_dropout_ln_bwd_kernel<P><<<grid, kWarpsPerCta * 32, 0, st>>>(dy, s, keep_mask, gamma, mean, rstd, dx, dbranch, \
-                                                                   partial_ws, rows, C, inv_keep)
+                                                                   partial_ws, rows, C, inv_keep, seed_dev, thresh)
   switch ((C + 127) / 128) {
     case 1: TFB200_BWD(1); break;
     case 2: TFB200_BWD(2); break;
@@ -351,6 +374,38 @@ int tfb200_add_dropout_layernorm_bwd_f32(const float* dy, const float* s, const 
   column_partials_finish_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial_ws, dgamma, dbeta, grid, 2 * C, C);
   msda_b200_count_launches(2);
   return int(cudaGetLastError());
+}
+
+int tfb200_add_dropout_layernorm_fwd_f32(const float* x, const float* branch, const uint8_t* keep_mask,
+                                         const float* gamma, const float* beta, float* s_out, float* y,
+                                         float* mean, float* rstd, int64_t rows, int C, float keep_prob, float eps,
+                                         void* stream) {
+  return ln_forward(x, branch, keep_mask, nullptr, gamma, beta, s_out, y, mean, rstd, rows, C, keep_prob, eps, stream);
+}
+
+int tfb200_add_dropout_layernorm_seeded_fwd_f32(const float* x, const float* branch, const int64_t* seed_dev,
+                                                const float* gamma, const float* beta, float* s_out, float* y,
+                                                float* mean, float* rstd, int64_t rows, int C, float keep_prob,
+                                                float eps, void* stream) {
+  if (!seed_dev) return TFB200_E_NULLPTR;
+  return ln_forward(x, branch, nullptr, seed_dev, gamma, beta, s_out, y, mean, rstd, rows, C, keep_prob, eps, stream);
+}
+
+int tfb200_add_dropout_layernorm_bwd_f32(const float* dy, const float* s, const uint8_t* keep_mask,
+                                         const float* gamma, const float* mean, const float* rstd, float* dx,
+                                         float* dbranch, float* dgamma, float* dbeta, float* partial_ws,
+                                         int64_t rows, int C, float keep_prob, void* stream) {
+  return ln_backward(dy, s, keep_mask, nullptr, gamma, mean, rstd, dx, dbranch, dgamma, dbeta, partial_ws, rows, C,
+                     keep_prob, stream);
+}
+
+int tfb200_add_dropout_layernorm_seeded_bwd_f32(const float* dy, const float* s, const int64_t* seed_dev,
+                                                const float* gamma, const float* mean, const float* rstd, float* dx,
+                                                float* dbranch, float* dgamma, float* dbeta, float* partial_ws,
+                                                int64_t rows, int C, float keep_prob, void* stream) {
+  if (!seed_dev) return TFB200_E_NULLPTR;
+  return ln_backward(dy, s, nullptr, seed_dev, gamma, mean, rstd, dx, dbranch, dgamma, dbeta, partial_ws, rows, C,
+                     keep_prob, stream);
 }
 
 int tfb200_colsum_f32(const float* x, float* out, float* partial_ws, int64_t rows, int C, void* stream) {
@@ -384,8 +439,7 @@ int tfb200_relu_dropout_fwd_f32(const float* a, float* h, const int64_t* seed_de
   if (n == 0) return 0;
   const int64_t n4 = n / 4;
   const int grid = int(n4 / 256 < 148 * 16 ? (n4 + 255) / 256 : 148 * 16);
-  const double t = double(keep_prob) * 4294967296.0;
-  const uint32_t thresh = t >= 4294967295.0 ? 0xffffffffu : uint32_t(t);
+  const uint32_t thresh = keep_threshold(keep_prob);
   relu_dropout_fwd_kernel<<<grid, 256, 0, cudaStream_t(stream)>>>(a, h, seed_dev, n4, training ? 1.f / keep_prob : 1.f,
                                                                   thresh, training);
   msda_b200_count_launches(1);

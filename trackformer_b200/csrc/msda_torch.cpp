@@ -335,6 +335,94 @@ void flat_adamw(at::Tensor param, const at::Tensor& grad, at::Tensor exp_avg, at
   TORCH_CHECK(rc == 0, "flat_adamw failed (code ", rc, ")");
 }
 
+// ---- frozen batch-norm + residual + ReLU over NHWC activations (backbone.py:46-55) ------------------------------------
+static bool nhwc_dense(const at::Tensor& t) {
+  return t.is_cuda() && t.scalar_type() == at::kFloat && t.dim() == 4 && t.is_contiguous(at::MemoryFormat::ChannelsLast);
+}
+
+at::Tensor frozen_bn_act_forward(const at::Tensor& x, const c10::optional<at::Tensor>& residual, const at::Tensor& scale,
+                                 const at::Tensor& shift, bool relu) {
+  TORCH_CHECK(nhwc_dense(x), "frozen_bn_act: x must be a channels-last fp32 CUDA tensor [N,C,H,W]");
+  const int64_t C = x.size(1);
+  TORCH_CHECK(C % 4 == 0 && scale.numel() == C && shift.numel() == C && scale.is_cuda() && shift.is_cuda() &&
+              scale.scalar_type() == at::kFloat && shift.scalar_type() == at::kFloat, "frozen_bn_act: bad scale/shift");
+  const float* res = nullptr;
+  if (residual.has_value()) {
+    TORCH_CHECK(nhwc_dense(*residual) && residual->sizes() == x.sizes(), "frozen_bn_act: residual must match x");
+    res = residual->data_ptr<float>();
+  }
+  const c10::cuda::CUDAGuard guard(x.device());
+  auto sc = scale.contiguous().view({C}), sh = shift.contiguous().view({C});
+  auto y = at::empty_like(x, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+  const int rc = tfb200_frozen_bn_act_fwd_f32(x.data_ptr<float>(), res, sc.data_ptr<float>(), sh.data_ptr<float>(),
+                                              y.data_ptr<float>(), x.numel() / C, int(C), relu ? 1 : 0,
+                                              at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "frozen_bn_act_forward failed (code ", rc, ")");
+  return y;
+}
+
+std::vector<at::Tensor> frozen_bn_act_backward(const at::Tensor& dy, const at::Tensor& y, const at::Tensor& scale, bool relu,
+                                               bool need_dx, bool need_dres) {
+  TORCH_CHECK(nhwc_dense(y) && dy.is_cuda() && dy.scalar_type() == at::kFloat && dy.sizes() == y.sizes(), "frozen_bn_act_backward: bad dy / y");
+  TORCH_CHECK(need_dx || need_dres, "frozen_bn_act_backward: nothing to compute");
+  const int64_t C = y.size(1);
+  const c10::cuda::CUDAGuard guard(y.device());
+  auto g = dy.contiguous(at::MemoryFormat::ChannelsLast);
+  auto sc = scale.contiguous().view({C});
+  at::Tensor dx, dres;
+  if (need_dx) dx = at::empty_like(y, y.options().memory_format(at::MemoryFormat::ChannelsLast));
+  if (need_dres) dres = at::empty_like(y, y.options().memory_format(at::MemoryFormat::ChannelsLast));
+  const int rc = tfb200_frozen_bn_act_bwd_f32(g.data_ptr<float>(), y.data_ptr<float>(), sc.data_ptr<float>(),
+                                              need_dx ? dx.data_ptr<float>() : nullptr,
+                                              need_dres ? dres.data_ptr<float>() : nullptr, y.numel() / C, int(C),
+                                              relu ? 1 : 0, at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "frozen_bn_act_backward failed (code ", rc, ")");
+  return {dx, dres};
+}
+
+// ---- residual + dropout + LayerNorm with mask-free (seeded) dropout --------------------------------------------------
+std::vector<at::Tensor> add_dropout_layernorm_seeded_forward(const at::Tensor& x, const at::Tensor& branch, const at::Tensor& seed,
+                                                             const at::Tensor& gamma, const at::Tensor& beta,
+                                                             double keep_prob, double eps) {
+  TORCH_CHECK(x.is_cuda() && branch.is_cuda(), "add_dropout_layernorm: CUDA tensors required (no CPU path)");
+  TORCH_CHECK(x.scalar_type() == at::kFloat && branch.scalar_type() == at::kFloat, "fp32 only");
+  TORCH_CHECK(x.sizes() == branch.sizes(), "x and branch must have the same shape");
+  TORCH_CHECK(seed.is_cuda() && seed.scalar_type() == at::kLong && seed.numel() >= 1, "seed must be an int64 CUDA tensor");
+  const int64_t C = x.size(-1);
+  const at::Tensor xc = x.contiguous(), bc = branch.contiguous(), g = gamma.contiguous(), b = beta.contiguous();
+  const int64_t rows = xc.numel() / C;
+  const c10::cuda::CUDAGuard guard(x.device());
+  at::Tensor y = at::empty_like(xc), s = at::empty_like(xc);
+  at::Tensor mean = at::empty({rows}, xc.options()), rstd = at::empty({rows}, xc.options());
+  const int rc = tfb200_add_dropout_layernorm_seeded_fwd_f32(
+      xc.data_ptr<float>(), bc.data_ptr<float>(), seed.data_ptr<int64_t>(), g.data_ptr<float>(), b.data_ptr<float>(),
+      s.data_ptr<float>(), y.data_ptr<float>(), mean.data_ptr<float>(), rstd.data_ptr<float>(), rows, int(C),
+      float(keep_prob), float(eps), c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "add_dropout_layernorm_seeded_forward failed (code ", rc, ")");
+  return {y, s, mean, rstd};
+}
+
+std::vector<at::Tensor> add_dropout_layernorm_seeded_backward(const at::Tensor& dy, const at::Tensor& s, const at::Tensor& seed,
+                                                              const at::Tensor& gamma, const at::Tensor& mean,
+                                                              const at::Tensor& rstd, double keep_prob) {
+  TORCH_CHECK(dy.is_cuda() && s.is_cuda(), "add_dropout_layernorm: CUDA tensors required (no CPU path)");
+  TORCH_CHECK(seed.is_cuda() && seed.scalar_type() == at::kLong && seed.numel() >= 1, "seed must be an int64 CUDA tensor");
+  const int64_t C = s.size(-1);
+  const at::Tensor dyc = dy.contiguous(), g = gamma.contiguous();
+  const int64_t rows = s.numel() / C;
+  const c10::cuda::CUDAGuard guard(s.device());
+  at::Tensor dx = at::empty_like(s), db = at::empty_like(s);
+  at::Tensor dgamma = at::empty({C}, s.options()), dbeta = at::empty({C}, s.options());
+  at::Tensor ws = at::empty({tfb200_ln_partial_ctas(rows), 2, C}, s.options());
+  const int rc = tfb200_add_dropout_layernorm_seeded_bwd_f32(
+      dyc.data_ptr<float>(), s.data_ptr<float>(), seed.data_ptr<int64_t>(), g.data_ptr<float>(), mean.data_ptr<float>(),
+      rstd.data_ptr<float>(), dx.data_ptr<float>(), db.data_ptr<float>(), dgamma.data_ptr<float>(),
+      dbeta.data_ptr<float>(), ws.data_ptr<float>(), rows, int(C), float(keep_prob),
+      c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "add_dropout_layernorm_seeded_backward failed (code ", rc, ")");
+  return {dx, db, dgamma, dbeta};
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200 (sm_100a) multi-scale deformable attention; drop-in for the reference extension";
   m.def("ms_deform_attn_forward", &ms_deform_attn_forward, "ms_deform_attn_forward");
@@ -346,6 +434,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ms_deform_attn_forward_enc", &ms_deform_attn_forward_enc);
   m.def("add_dropout_layernorm_forward", &add_dropout_layernorm_forward);
   m.def("add_dropout_layernorm_backward", &add_dropout_layernorm_backward);
+  m.def("add_dropout_layernorm_seeded_forward", &add_dropout_layernorm_seeded_forward);
+  m.def("add_dropout_layernorm_seeded_backward", &add_dropout_layernorm_seeded_backward);
   m.def("colsum", &colsum);
   m.def("lsa", &lsa);
   m.def("sampling_prep_forward", &sampling_prep_forward);
@@ -354,4 +444,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("relu_dropout_backward", &relu_dropout_backward);
   m.def("detect_postprocess", &detect_postprocess);
   m.def("flat_adamw", &flat_adamw);
+  m.def("frozen_bn_act_forward", &frozen_bn_act_forward);
+  m.def("frozen_bn_act_backward", &frozen_bn_act_backward);
 }

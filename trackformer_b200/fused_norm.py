@@ -9,12 +9,37 @@ CUDA only -- on other devices / unsupported widths it defers to the stock PyTorc
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import ext
+
+# mask-free dropout (hash of a per-call device seed and the element index, like fused_linear.relu_dropout) instead of a
+# bernoulli_ mask tensor per call; TFB200_LN_SEEDED=0 keeps the mask route
+_SEEDED = os.environ.get("TFB200_LN_SEEDED", "1") != "0"
+
+
+class _AddDropoutLayerNormSeeded(Function):
+    @staticmethod
+    def forward(ctx, x, branch, gamma, beta, p, eps):
+        keep = 1.0 - p
+        seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=x.device)
+        y, s, mean, rstd = ext.load().add_dropout_layernorm_seeded_forward(x, branch, seed, gamma, beta, keep, eps)
+        ctx.save_for_backward(s, mean, rstd, gamma, seed)
+        ctx.keep = keep
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        s, mean, rstd, gamma, seed = ctx.saved_tensors
+        dx, dbranch, dgamma, dbeta = ext.load().add_dropout_layernorm_seeded_backward(dy, s, seed, gamma, mean, rstd,
+                                                                                      ctx.keep)
+        return dx, dbranch, dgamma, dbeta, None, None
 
 
 class _AddDropoutLayerNorm(Function):
@@ -47,6 +72,8 @@ def supported(x: torch.Tensor, norm: nn.LayerNorm) -> bool:
 def add_dropout_layernorm(x: torch.Tensor, branch: torch.Tensor, dropout: nn.Dropout, norm: nn.LayerNorm) -> torch.Tensor:
     """``norm(x + dropout(branch))`` -- fused when the geometry allows, the module chain otherwise."""
     if supported(x, norm) and branch.shape == x.shape:
+        if _SEEDED and dropout.training and dropout.p > 0.0:
+            return _AddDropoutLayerNormSeeded.apply(x, branch, norm.weight, norm.bias, float(dropout.p), float(norm.eps))
         return _AddDropoutLayerNorm.apply(x, branch, norm.weight, norm.bias, float(dropout.p),
                                           bool(dropout.training), float(norm.eps))
     return norm(x + dropout(branch))
