@@ -37,6 +37,11 @@ def _newer(target: str, sources) -> bool:
     return all(os.path.getmtime(s) <= t for s in sources)
 
 
+def _public_headers():
+    inc = os.path.join(ROOT, "include")
+    return [os.path.join(inc, f) for f in sorted(os.listdir(inc)) if f.endswith(".h")]
+
+
 def _run(cmd, verbose):
     if verbose:
         print("+", " ".join(cmd), flush=True)
@@ -44,8 +49,8 @@ def _run(cmd, verbose):
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))]
-    srcs.append(os.path.join(ROOT, "include", "msda_b200.h"))
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    srcs += _public_headers()
     if not force and _newer(LIB_SO, srcs):
         return LIB_SO
     cu = [s for s in srcs if s.endswith(".cu")]
@@ -57,7 +62,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 def build_extension(force: bool = False, verbose: bool = False) -> str:
     build_library(False, verbose)
     src = os.path.join(CSRC, "msda_torch.cpp")
-    if not force and _newer(EXT_SO, [src, LIB_SO, os.path.join(ROOT, "include", "msda_b200.h")]):
+    hdrs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".h")]
+    if not force and _newer(EXT_SO, [src, LIB_SO, *hdrs, *_public_headers()]):
         return EXT_SO
     import torch
     from torch.utils import cpp_extension as ce
