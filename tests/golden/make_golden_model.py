@@ -73,6 +73,11 @@ def main():
         "track_multi_frame": lambda: mf.run_two_frame_tracking(build, (128, 160), 9, multi_frame=True),
         "train_step_det": lambda: mf.run_train_step(build, [(160, 224), (160, 224)], 6),
         "train_step_tracking": lambda: mf.run_train_step(build, [(128, 160)], 7, tracking=True),
+        # BASELINE.json configs[1], [2], [4] at their full sizes (outputs only; a few hundred KB each)
+        "det_c2_800x1333": lambda: mf.run_detection(build, [(800, 1333)]),
+        "train_step_c2": lambda: mf.run_train_step(build, [(800, 1333)], 20, optimizer=True),
+        "track_c3_800x1333": lambda: mf.run_two_frame_tracking(build, (800, 1333), 100),
+        "track_c5_1080x1920": lambda: mf.run_two_frame_tracking(build, (1080, 1920), 300, multi_frame=True),
     }
     only = sys.argv[1:]
     for name, fn in cases.items():

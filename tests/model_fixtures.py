@@ -130,8 +130,26 @@ def run_two_frame_tracking(build, size, n_track, device="cpu", seed=0, multi_fra
             "f2_hs_mean": _to_np(out2["hs_embed"].mean(-1)), "n_levels_memory": len(memory2)}
 
 
-def run_train_step(build, sizes, n_boxes, device="cpu", seed=0, tracking=False, **overrides):
-    """One forward + criterion + backward with dropout disabled (module in train mode)."""
+def reference_optimizer_groups(model, lr=2e-4, lr_backbone=2e-5, lr_linear_proj_mult=0.1, weight_decay=1e-4):
+    """The three AdamW parameter groups of the reference's src/train.py:100-119 with the defaults of
+    cfgs/train.yaml:1-10 (names containing 'backbone.0' -> lr_backbone; 'reference_points' /
+    'sampling_offsets' -> lr * lr_linear_proj_mult)."""
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    bb, lin = ("backbone.0",), ("reference_points", "sampling_offsets")
+
+    def hit(n, keys):
+        return any(k in n for k in keys)
+    return [{"params": [p for n, p in named if not hit(n, bb + lin + ("layers_track_attention",))], "lr": lr,
+             "weight_decay": weight_decay},
+            {"params": [p for n, p in named if hit(n, bb)], "lr": lr_backbone, "weight_decay": weight_decay},
+            {"params": [p for n, p in named if hit(n, lin)], "lr": lr * lr_linear_proj_mult,
+             "weight_decay": weight_decay}]
+
+
+def run_train_step(build, sizes, n_boxes, device="cpu", seed=0, tracking=False, optimizer=False, **overrides):
+    """One forward + criterion + backward with dropout disabled (module in train mode).  With ``optimizer``
+    the reference's clip_grad_norm_(0.1) + AdamW step (engine.py:147-151, train.py:100-119) follows and the
+    updated values of the GRAD_KEYS parameters are recorded as ``param/<key>``."""
     model, criterion = build(tracking, False, dropout=0.0, **overrides)
     canonical_weights_(model, seed)
     model.to(device).train()
@@ -165,6 +183,14 @@ def run_train_step(build, sizes, n_boxes, device="cpu", seed=0, tracking=False, 
             res["grad/" + k] = _to_np(named[k].grad)
     sq = sum(float((p.grad.double() ** 2).sum()) for p in model.parameters() if p.grad is not None)
     res["grad_global_norm"] = torch.tensor(sq).sqrt().numpy()
+    if optimizer:
+        opt = torch.optim.AdamW(reference_optimizer_groups(model), lr=2e-4, weight_decay=1e-4)
+        before = {k: named[k].detach().clone() for k in GRAD_KEYS if k in named}
+        torch.nn.utils.clip_grad_norm_([p for p in model.parameters() if p.requires_grad], 0.1)
+        opt.step()
+        for k, b in before.items():
+            res["param/" + k] = _to_np(named[k])
+            res["param_before/" + k] = _to_np(b)
     if tracking:
         for i, t in enumerate(targets_out):
             for key in ("track_query_match_ids", "track_queries_mask", "track_queries_fal_pos_mask"):

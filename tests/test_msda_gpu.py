@@ -376,8 +376,7 @@ TILE_CASES = {
 
 @pytest.mark.parametrize("name", sorted(TILE_CASES))
 def test_tiled_encoder_forward_equals_general_kernel(msda, dev, name):
-    """Same taps, same accumulation order: the shared-memory tiled kernel must reproduce the general d32 kernel
-    bit for bit, and both must match the oracle."""
+    """The shared-memory tiled kernel against the default kernel (same taps) and against the oracle."""
     from oracle import msda_oracle
     N, M, hw, P, dist = TILE_CASES[name]
     g = torch.Generator().manual_seed(len(name))
@@ -400,6 +399,101 @@ def test_tiled_encoder_forward_equals_general_kernel(msda, dev, name):
     flat_hw = [int(v) for pair in hw for v in pair]
     tiled = msda.ms_deform_attn_forward_enc(tv, ts, tl, ta, flat_hw, 64)
     general = msda.ms_deform_attn_forward(tv, ts, tl, ta, 64)
-    assert torch.equal(tiled, general)
+    torch.testing.assert_close(tiled, general, rtol=1e-5, atol=1e-5)     # different summation order, same taps
     ref_out = msda_oracle.msda_forward(value.numpy(), shapes.numpy(), loc.numpy(), attn.numpy())
     np.testing.assert_allclose(tiled.cpu().numpy(), ref_out, **F32)
+
+
+# ----------------------------------------------------------------------------- every fp32 / D = 32 kernel family
+def _encoder_problem(name):
+    N, M, hw, P, dist = TILE_CASES[name]
+    g = torch.Generator().manual_seed(100 + len(name))
+    shapes = torch.as_tensor(hw, dtype=torch.long)
+    L = len(hw)
+    S = int((shapes[:, 0] * shapes[:, 1]).sum())
+    value = torch.randn(N, S, M, 32, generator=g)
+    if dist == "uniform":
+        loc = torch.rand(N, S, M, L, P, 2, generator=g) * 1.2 - 0.1
+    else:
+        refs = []
+        for (h, w) in hw:
+            ys, xs = torch.meshgrid(torch.arange(h) + 0.5, torch.arange(w) + 0.5, indexing="ij")
+            refs.append(torch.stack([xs.reshape(-1) / w, ys.reshape(-1) / h], -1))
+        ref = torch.cat(refs, 0)[None, :, None, None, None, :]
+        # smooth offsets (what a model produces: neighbouring queries sample neighbouring windows, so the run
+        # kernels take their "same window" / "slide by one" paths) plus a little per-sample jitter
+        base = torch.randn(1, 1, M, L, P, 2, generator=g) * 2.5
+        off = base + 0.2 * torch.randn(N, S, M, L, P, 2, generator=g)
+        loc = ref + off / shapes.flip(-1).float()[None, None, None, :, None, :]
+    attn = torch.softmax(torch.randn(N, S, M, L * P, generator=g), -1).view(N, S, M, L, P)
+    attn[:, ::7, 1] = 0.0                                     # exact-zero attention rows (skipped reductions)
+    gout = torch.randn(N, S, M * 32, generator=g)
+    return value, shapes, loc, attn, gout
+
+
+# 0 = automatic choice, 100 / 101 = run kernels (R = 8 / 4), 110 = warp-per-group kernels, 20 = 8-lane-group kernels
+@pytest.mark.parametrize("variant", [0, 100, 101, 110, 20])
+@pytest.mark.parametrize("name", sorted(TILE_CASES))
+def test_kernel_families_match_c_oracle(msda, dev, name, variant):
+    """Forward and fused backward of every specialised kernel family on encoder-shaped problems (incl. the FULL
+    C2 encoder call, batch 2) against the C restatement of the reference kernels."""
+    from oracle import msda_oracle
+    value, shapes, loc, attn, gout = _encoder_problem(name)
+    ref_out = msda_oracle.msda_forward(value.numpy(), shapes.numpy(), loc.numpy(), attn.numpy())
+    ref_gv, ref_gl, ref_ga = msda_oracle.msda_backward(value.numpy(), shapes.numpy(), loc.numpy(), attn.numpy(),
+                                                       gout.numpy())
+    tv, ts, tl, ta, tg = (x.to(dev) for x in (value, shapes, loc, attn, gout))
+    msda.set_variant(variant, variant)
+    try:
+        out = msda.ms_deform_attn_forward(tv, ts, tl, ta, 64)
+        gv, gl, ga = msda.ms_deform_attn_backward(tv, ts, tl, ta, tg, 64)
+        torch.cuda.synchronize()
+    finally:
+        msda.set_variant(0, 0)
+    np.testing.assert_allclose(out.cpu().numpy(), ref_out, **F32)
+    scale = max(1.0, float(np.abs(ref_gv).max()))
+    np.testing.assert_allclose(gv.cpu().numpy(), ref_gv, rtol=F32["rtol"], atol=F32["atol"] * scale)
+    np.testing.assert_allclose(ga.cpu().numpy(), ref_ga, **F32)
+    np.testing.assert_allclose(gl.cpu().numpy(), ref_gl, rtol=F32["rtol"] * 5, atol=F32["atol"] * 50)
+
+
+@pytest.mark.parametrize("variant", [100, 101, 110])
+def test_kernel_families_on_degenerate_and_ragged_shapes(msda, dev, variant):
+    """levels with a single row / column (on-the-fly predicated path), Lq not a multiple of the run block, M = 4 and
+    12 heads, L*P = 64 (the largest supported; > 48 KB of dynamic shared memory), out-of-range locations"""
+    from oracle import msda_oracle
+    cases = [(2, 8, 77, [(1, 7), (6, 1), (2, 2), (5, 9)], 2), (1, 4, 1000, [(9, 11), (5, 6)], 4),
+             (1, 12, 301, [(12, 16), (6, 8), (3, 4)], 3), (1, 8, 190, [(6, 8), (3, 4)] * 4, 8)]
+    for i, (N, M, Lq, hw, P) in enumerate(cases):
+        value, shapes, loc, attn, gout = rand_problem(50 + i, N, M, 32, Lq, hw, P, np.float32, lo=-0.3, hi=1.3)
+        ref_out = msda_oracle.msda_forward(value, shapes, loc, attn)
+        ref_gv, ref_gl, ref_ga = msda_oracle.msda_backward(value, shapes, loc, attn, gout)
+        tv, ts, tl, ta, tg = (torch.from_numpy(x).to(dev) for x in (value, shapes, loc, attn, gout))
+        msda.set_variant(variant, variant)
+        try:
+            out = msda.ms_deform_attn_forward(tv, ts, tl, ta, 64)
+            gv, gl, ga = msda.ms_deform_attn_backward(tv, ts, tl, ta, tg, 64)
+            torch.cuda.synchronize()
+        finally:
+            msda.set_variant(0, 0)
+        np.testing.assert_allclose(out.cpu().numpy(), ref_out, **F32, err_msg=str(i))
+        scale = max(1.0, float(np.abs(ref_gv).max()))
+        np.testing.assert_allclose(gv.cpu().numpy(), ref_gv, rtol=F32["rtol"], atol=F32["atol"] * scale, err_msg=str(i))
+        np.testing.assert_allclose(ga.cpu().numpy(), ref_ga, **F32, err_msg=str(i))
+        np.testing.assert_allclose(gl.cpu().numpy(), ref_gl, rtol=F32["rtol"] * 5, atol=F32["atol"] * 50, err_msg=str(i))
+
+
+def test_d32_kernels_with_64_samples_per_query(msda, dev):
+    """the 8-lane-group backward needs > 48 KB of dynamic shared memory once L*P >= 38"""
+    from oracle import msda_oracle
+    value, shapes, loc, attn, gout = rand_problem(64, 1, 8, 32, 130, [(6, 8), (3, 4)] * 4, 8, np.float32)
+    ref_gv, ref_gl, ref_ga = msda_oracle.msda_backward(value, shapes, loc, attn, gout)
+    tv, ts, tl, ta, tg = (torch.from_numpy(x).to(dev) for x in (value, shapes, loc, attn, gout))
+    msda.set_variant(20, 20)
+    try:
+        gv, gl, ga = msda.ms_deform_attn_backward(tv, ts, tl, ta, tg, 64)
+        torch.cuda.synchronize()
+    finally:
+        msda.set_variant(0, 0)
+    np.testing.assert_allclose(ga.cpu().numpy(), ref_ga, **F32)
+    np.testing.assert_allclose(gv.cpu().numpy(), ref_gv, rtol=F32["rtol"], atol=F32["atol"] * max(1.0, float(np.abs(ref_gv).max())))

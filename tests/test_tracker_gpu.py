@@ -118,12 +118,33 @@ def test_graph_replay_matches_eager_tracker(dev, multi_frame):
     det = detectors[0]
     assert det.replays == 6 and 1 <= det.captures <= 6
     assert len(eager["rows"]) > 0
-    if margin < 1.5e-5:
-        pytest.skip(f"eager run has a decision {margin:.1e} from its threshold: ids may legitimately differ")
+
+    # (1) deterministic part, never skipped: the same padded program run WITHOUT graphs (GraphedDetector(use_graphs=False)
+    #     keeps the filler queries) executes the same kernels on the same inputs -> identical decisions and values.
+    class PaddedEagerTracker(Tracker):
+        def __init__(self, model, post, cfg_, attn):
+            super().__init__(GraphedDetector(model, bucket=16, use_graphs=False), post, cfg_, attn)
+    padded = tf.run_model_sequence(build, PaddedEagerTracker, DeformablePostProcess(), cfg, size=size, n_frames=6,
+                                   device=dev, multi_frame=multi_frame)
     for key in ("num_reids", "track_num", "active_ids", "inactive_ids"):
-        np.testing.assert_array_equal(graphed[key], eager[key], err_msg=key)
-    np.testing.assert_array_equal(graphed["rows"][:, :3], eager["rows"][:, :3])
-    np.testing.assert_allclose(graphed["rows"][:, 3:], eager["rows"][:, 3:], rtol=1e-4, atol=1e-3)
+        np.testing.assert_array_equal(graphed[key], padded[key], err_msg=key)
+    np.testing.assert_array_equal(graphed["rows"][:, :3], padded["rows"][:, :3])
+    np.testing.assert_allclose(graphed["rows"][:, 3:], padded["rows"][:, 3:], rtol=1e-6, atol=1e-6)
+
+    # (2) against the UNPADDED eager model the filler queries change the fp32 summation order of the masked softmax
+    #     (~4e-6 on a score): ids can only be required to agree when no decision of the eager run sits inside that noise.
+    if margin >= 1.5e-5:
+        for key in ("num_reids", "track_num", "active_ids", "inactive_ids"):
+            np.testing.assert_array_equal(graphed[key], eager[key], err_msg=key)
+        np.testing.assert_array_equal(graphed["rows"][:, :3], eager["rows"][:, :3])
+        np.testing.assert_allclose(graphed["rows"][:, 3:], eager["rows"][:, 3:], rtol=1e-4, atol=1e-3)
+    else:
+        print(f"eager run has a decision {margin:.1e} from its threshold: unpadded-id comparison replaced by the "
+              f"frame-1 value comparison (test_graph_replay_outputs_match_eager_forward covers the numerics)")
+        first = eager["rows"][:, 1] == eager["rows"][:, 1].min()          # columns: id, frame, obj_ind, score, box
+        gfirst = graphed["rows"][:, 1] == graphed["rows"][:, 1].min()
+        assert first.sum() == gfirst.sum()           # frame 1 has no track queries yet -> no padding -> same program
+        np.testing.assert_allclose(graphed["rows"][gfirst][:, 3:], eager["rows"][first][:, 3:], rtol=1e-5, atol=1e-5)
 
 
 def test_graph_replay_outputs_match_eager_forward(dev):

@@ -27,6 +27,11 @@ C5 = [(135, 240), (68, 120), (34, 60), (17, 30)]
 CASES = {
     "c2_enc_model": (1, 8, 32, C2, 4, None, "model"),
     "c2_enc_uniform": (1, 8, 32, C2, 4, None, "uniform"),
+    # what bench.py's random-init model produces: sampling_offsets.weight = 0, bias = the 8-direction grid
+    # (ms_deform_attn.py:34-42) -> every query samples the same pattern around its own reference point
+    "c2_enc_init": (1, 8, 32, C2, 4, None, "model0"),
+    "c2_enc_smooth": (1, 8, 32, C2, 4, None, "model0.1"),
+    "c2_enc_init_n2": (2, 8, 32, C2, 4, None, "model0"),
     "c2_enc_model_n2": (2, 8, 32, C2, 4, None, "model"),
     "c2_dec": (1, 8, 32, C2, 4, 300, "boxes"),
     "c2_dec_n2": (2, 8, 32, C2, 4, 300, "boxes"),
@@ -71,7 +76,8 @@ def make_case(name, dev, seed=0):
             ref = torch.cat(refs, 0)[None, :, None, None, None, :].expand(N, S, 1, L, 1, 2)
             off = (HEAD_DIRS[torch.arange(M) % 8][None, None, :, None, None, :]
                    * torch.arange(1, P + 1, dtype=torch.float32)[None, None, None, None, :, None])
-            off = off + 0.5 * torch.randn(N, Lq, M, L, P, 2, generator=g)          # "trained" jitter
+            jitter = float(dist[5:]) if len(dist) > 5 else 0.5
+            off = off + jitter * torch.randn(N, Lq, M, L, P, 2, generator=g)       # "trained" per-sample jitter (pixels)
             # the reference normalises (x, y) offsets by (H, W) -- ops/modules/ms_deform_attn.py:78-79
             norm = shapes.to(torch.float32)[None, None, None, :, None, :]
             loc = ref + off / norm

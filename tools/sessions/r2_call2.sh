@@ -1,0 +1,27 @@
+#!/bin/bash
+# Round 2, call 2: new MSDeformAttn kernel families (run / wide) -- parity, op benchmark; plus the prep-work A/B.
+set -u
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
+echo "=== op tests"
+timeout 1200 python -m pytest tests/test_msda_gpu.py -q -x 2>&1 | tail -8
+echo "=== opbench"
+timeout 900 python tools/opbench.py --cases c2_enc_init,c2_enc_smooth,c2_enc_model,c2_enc_uniform,c2_dec,c2_enc_init_n2,c2_dec_n2 \
+   --variants 0,100,101,110,20 --bwd-variants 0,100,101,110,20 --iters 20 --out gpurun_out/r2_opbench_v1.json 2>&1 | cut -c1-230
+echo "=== prep tests"
+timeout 900 python -m pytest tests/test_fused_bn_gpu.py tests/test_fused_norm_gpu.py tests/test_train_step_gpu.py -q 2>&1 | tail -5
+run() {
+  local name=$1; shift
+  env "$@" timeout 600 python bench.py --steps 40 --warmup 5 --no-cpu-baseline 2>gpurun_out/bench_r2_${name}.err | tee gpurun_out/bench_r2_${name}.json | cut -c1-170
+}
+run all_on      TFB200_FUSED_BN=1 TFB200_GATHER_GRADS=1 TFB200_LN_SEEDED=1
+run no_fused_bn TFB200_FUSED_BN=0 TFB200_GATHER_GRADS=1 TFB200_LN_SEEDED=1
+run no_gather   TFB200_FUSED_BN=1 TFB200_GATHER_GRADS=0 TFB200_LN_SEEDED=1
+run no_seeded   TFB200_FUSED_BN=1 TFB200_GATHER_GRADS=1 TFB200_LN_SEEDED=0
+echo "=== model parity (incl. the new full-size cases)"
+timeout 1500 python -m pytest tests/test_model_parity_gpu.py tests/test_tracker_gpu.py -q -s 2>&1 | grep -v "^$" | tail -40
+echo "=== ncu launch list of the step graph (kernel nodes)"
+timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -c 14000 --csv \
+  --log-file gpurun_out/r2_launches_head.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+wc -l gpurun_out/r2_launches_head.csv
+gzip -f gpurun_out/r2_launches_head.csv

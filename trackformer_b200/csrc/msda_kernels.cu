@@ -28,6 +28,7 @@
 #include "msda_common.cuh"
 #include "msda_d32.cuh"
 #include "msda_d36.cuh"
+#include "msda_run.cuh"
 #include "msda_tile.cuh"
 
 namespace msda {
@@ -224,6 +225,29 @@ static int check_dims(const Dims& d) {
 template <typename T>
 static bool aligned16(const T* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Opts `kernel` in to `bytes` of dynamic shared memory when that exceeds the 48 KB default (the attribute is sticky,
+// so it is raised at most a few times per kernel over the life of the process).
+template <typename K>
+static cudaError_t ensure_dyn_smem(K kernel, size_t bytes, std::atomic<size_t>& granted) {
+  if (bytes <= 48 * 1024 || bytes <= granted.load(std::memory_order_relaxed)) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  if (e == cudaSuccess) granted.store(bytes, std::memory_order_relaxed);
+  return e;
+}
+#define MSDA_ENSURE_SMEM(kernel, bytes)                                         \
+  do {                                                                          \
+    static std::atomic<size_t> granted__{0};                                    \
+    cudaError_t e__ = ensure_dyn_smem(kernel, bytes, granted__);                \
+    if (e__ != cudaSuccess) return int(e__);                                    \
+  } while (0)
+
+// Which specialised fp32 / D = 32 kernel family serves a problem (variant 0 = automatic):
+//   run  : large query sets (encoder) -- register-resident sliding windows over runs of consecutive queries
+//   wide : small query sets (decoder) -- one warp per (n, q, m) group
+//   d32  : everything in between (and M % 4 != 0): one 8-lane group per (n, q, m), tap tables in shared memory
+enum class Family { kD32, kRun8, kRun4, kWide };
+static Family pick_family(int variant, int64_t groups, const struct Dims& d);
+
 #define MSDA_LAUNCH_FWD(VEC_, G_, IT_)                                                       \
   msda_fwd_kernel<T, VEC_, G_, IT_><<<grid_for(G_), kThreads, 0, st>>>(                      \
       value, shapes, loc, attn, out, d.S, d.M, d.D, d.L, d.Lq, d.P, groups)
@@ -248,6 +272,17 @@ static void pick_shape(int npacks, int* G, int* iters) {
   *iters = (npacks + g - 1) / g;
 }
 
+static Family pick_family(int variant, int64_t groups, const Dims& d) {
+  const bool run_ok = (d.M % kRunHeads == 0);
+  if (variant == 100) return run_ok ? Family::kRun8 : Family::kD32;
+  if (variant == 101) return run_ok ? Family::kRun4 : Family::kD32;
+  if (variant == 110) return Family::kWide;
+  if (variant != 0) return Family::kD32;                    // the older tuning codes address the d32 kernels
+  if (groups <= 32768) return Family::kWide;
+  if (run_ok && d.Lq >= 2048) return Family::kRun8;
+  return Family::kD32;
+}
+
 template <typename T>
 static int forward_impl(const T* value, const int64_t* shapes, const T* loc, const T* attn, T* out,
                         const Dims& d, cudaStream_t st) {
@@ -265,15 +300,47 @@ static int forward_impl(const T* value, const int64_t* shapes, const T* loc, con
     const int LP = d.L * d.P;
     if (variant != 1 && vec_ok && d.D == 32 && LP <= kMaxLP && aligned16(loc) && aligned16(attn) &&
         groups < (int64_t(1) << 31)) {
+      const Family fam = pick_family(variant, groups, d);
+      if (fam == Family::kRun8 || fam == Family::kRun4) {
+        const int R = fam == Family::kRun8 ? 8 : 4;
+        const int qblocks = (d.Lq + 4 * R - 1) / (4 * R);
+        const int64_t units = int64_t(d.N) * qblocks * (d.M / kRunHeads);
+        if (units < (int64_t(1) << 31)) {
+          const size_t smem = fwd_run_smem_bytes(R, LP);
+#define MSDA_FWD_RUN(R_, LPCT_)                                                                                     \
+  do {                                                                                                              \
+    MSDA_ENSURE_SMEM((msda_fwd_run_kernel<R_, LPCT_>), smem);                                                       \
+    msda_fwd_run_kernel<R_, LPCT_><<<unsigned(units), kRunThreads, smem, st>>>(value, shapes, loc, attn, out, d.S,   \
+                                                                              d.M, d.L, d.Lq, d.P, qblocks);        \
+  } while (0)
+          if (R == 8 && LP == 16) MSDA_FWD_RUN(8, 16);
+          else if (R == 8) MSDA_FWD_RUN(8, 0);
+          else if (LP == 16) MSDA_FWD_RUN(4, 16);
+          else MSDA_FWD_RUN(4, 0);
+#undef MSDA_FWD_RUN
+          g_launches.fetch_add(1, std::memory_order_relaxed);
+          return int(cudaGetLastError());
+        }
+      }
+      if (fam == Family::kWide) {
+        const unsigned grid = unsigned((groups + kWideThreads / 32 - 1) / (kWideThreads / 32));
+        msda_fwd_wide_kernel<<<grid, kWideThreads, 0, st>>>(value, shapes, loc, attn, out, d.S, d.M, d.L, d.Lq, d.P,
+                                                            uint32_t(groups));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return int(cudaGetLastError());
+      }
       const int64_t ctas = (groups + kGroupsPerCta - 1) / kGroupsPerCta;
       // variant = 10 * tuning + iters_code: iters_code >= 2 forces iters = code - 1; tuning picks (unroll, min CTAs/SM)
-      const int tuning = variant / 10, icode = variant % 10;
+      const int tuning = variant >= 100 ? 0 : variant / 10, icode = variant >= 100 ? 0 : variant % 10;
       const int iters = icode >= 2 ? icode - 1 : pick_iters(ctas);
       const unsigned grid = unsigned((ctas + iters - 1) / iters);
       const size_t smem = fwd_d32_smem_bytes(LP);
 #define MSDA_FWD_D32(U, B)                                                                                          \
-  msda_fwd_d32_kernel<256, U, B><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, out, d.S, d.M, d.L, d.Lq, \
-                                                                  d.P, uint32_t(groups), iters)
+  do {                                                                                                              \
+    MSDA_ENSURE_SMEM((msda_fwd_d32_kernel<256, U, B>), smem);                                                       \
+    msda_fwd_d32_kernel<256, U, B><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, out, d.S, d.M, d.L,    \
+                                                                    d.Lq, d.P, uint32_t(groups), iters);            \
+  } while (0)
       if (d.M == 8 && tuning == 1) MSDA_FWD_D32(2, 5);
       else if (d.M == 8 && tuning == 2) MSDA_FWD_D32(2, 6);
       else if (d.M == 8 && tuning == 3) MSDA_FWD_D32(4, 5);
@@ -284,9 +351,11 @@ static int forward_impl(const T* value, const int64_t* shapes, const T* loc, con
       else if (d.M == 8 && tuning == 8) MSDA_FWD_D32(4, 1);
       else if (d.M == 8) MSDA_FWD_D32(4, 4);          // measured best overall (profiles/): 64 registers, 4 CTAs/SM
 #undef MSDA_FWD_D32
-      else
+      else {
+        MSDA_ENSURE_SMEM((msda_fwd_d32_kernel<0>), smem);
         msda_fwd_d32_kernel<0><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, out, d.S, d.M, d.L, d.Lq,
                                                                 d.P, uint32_t(groups), iters);
+      }
       launched = true;
     }
   }
@@ -353,23 +422,57 @@ static int backward_impl(const T* value, const int64_t* shapes, const T* loc, co
     const int LP = d.L * d.P;
     if (variant != 1 && vec_ok && d.D == 32 && LP <= kMaxLP && aligned16(loc) && aligned16(attn) &&
         aligned16(gloc) && aligned16(gattn) && groups < (int64_t(1) << 31)) {
+      const Family fam = pick_family(variant, groups, d);
+      if (fam == Family::kRun8 || fam == Family::kRun4) {
+        const int R = fam == Family::kRun8 ? 8 : 4;
+        const int qblocks = (d.Lq + 4 * R - 1) / (4 * R);
+        const int64_t units = int64_t(d.N) * qblocks * (d.M / kRunHeads);
+        if (units < (int64_t(1) << 31)) {
+          const size_t smem = bwd_run_smem_bytes(R, LP);
+#define MSDA_BWD_RUN(R_, LPCT_)                                                                                     \
+  do {                                                                                                              \
+    MSDA_ENSURE_SMEM((msda_bwd_run_kernel<R_, LPCT_>), smem);                                                       \
+    msda_bwd_run_kernel<R_, LPCT_><<<unsigned(units), kRunThreads, smem, st>>>(                                     \
+        value, shapes, loc, attn, gout, gval, gloc, gattn, d.S, d.M, d.L, d.Lq, d.P, qblocks);                      \
+  } while (0)
+          if (R == 8 && LP == 16) MSDA_BWD_RUN(8, 16);
+          else if (R == 8) MSDA_BWD_RUN(8, 0);
+          else if (LP == 16) MSDA_BWD_RUN(4, 16);
+          else MSDA_BWD_RUN(4, 0);
+#undef MSDA_BWD_RUN
+          g_launches.fetch_add(1, std::memory_order_relaxed);
+          return int(cudaGetLastError());
+        }
+      }
+      if (fam == Family::kWide) {
+        const unsigned grid = unsigned((groups + kWideThreads / 32 - 1) / (kWideThreads / 32));
+        msda_bwd_wide_kernel<<<grid, kWideThreads, 0, st>>>(value, shapes, loc, attn, gout, gval, gloc, gattn, d.S, d.M,
+                                                            d.L, d.Lq, d.P, uint32_t(groups));
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        return int(cudaGetLastError());
+      }
       const int64_t ctas = (groups + kGroupsPerCta - 1) / kGroupsPerCta;
-      const int tuning = variant / 10, icode = variant % 10;
+      const int tuning = variant >= 100 ? 0 : variant / 10, icode = variant >= 100 ? 0 : variant % 10;
       const int iters = icode >= 2 ? icode - 1 : pick_iters(ctas);
       const unsigned grid = unsigned((ctas + iters - 1) / iters);
       const size_t smem = bwd_d32_smem_bytes(LP);
 #define MSDA_BWD_D32(B)                                                                                              \
-  msda_bwd_d32_kernel<256, B><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, gout, gval, gloc, gattn, d.S, \
-                                                               d.M, d.L, d.Lq, d.P, uint32_t(groups), iters)
+  do {                                                                                                               \
+    MSDA_ENSURE_SMEM((msda_bwd_d32_kernel<256, B>), smem);                                                           \
+    msda_bwd_d32_kernel<256, B><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, gout, gval, gloc, gattn,   \
+                                                                 d.S, d.M, d.L, d.Lq, d.P, uint32_t(groups), iters); \
+  } while (0)
       if (d.M == 8 && tuning == 1) MSDA_BWD_D32(2);
       else if (d.M == 8 && tuning == 2) MSDA_BWD_D32(3);
       else if (d.M == 8 && tuning == 3) MSDA_BWD_D32(5);
       else if (d.M == 8 && tuning == 4) MSDA_BWD_D32(6);
       else if (d.M == 8) MSDA_BWD_D32(4);
 #undef MSDA_BWD_D32
-      else
+      else {
+        MSDA_ENSURE_SMEM((msda_bwd_d32_kernel<0>), smem);
         msda_bwd_d32_kernel<0><<<grid, kD32Threads, smem, st>>>(value, shapes, loc, attn, gout, gval, gloc, gattn,
                                                                 d.S, d.M, d.L, d.Lq, d.P, uint32_t(groups), iters);
+      }
       launched = true;
     }
   }

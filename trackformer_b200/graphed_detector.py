@@ -36,6 +36,9 @@ class GraphedDetector:
         self.use_graphs = use_graphs
         self.warmup = warmup
         self.multi_frame = bool(getattr(model, "multi_frame_attention", False))
+        # models that read prev_features (deformable_detr.py `_project_levels`): multi-frame attention and/or merged
+        # frame features -- both must see the caller's previous-frame maps, and both keep what we return across frames
+        self.uses_prev = self.multi_frame or bool(getattr(model, "merge_frame_features", False))
         self._plans = {}
         self.replays = 0
         self.captures = 0
@@ -117,7 +120,7 @@ class GraphedDetector:
         if targets is not None and "track_query_boxes" in targets[0]:
             k = int(targets[0]["track_query_boxes"].shape[0])
         kb = self._padded_count(k)
-        use_prev = self.multi_frame and prev_features is not None
+        use_prev = self.uses_prev and prev_features is not None
         key = (tuple(samples.shape), samples.dtype, kb, use_prev)
         plan = self._plans.get(key)
         if plan is None:
@@ -148,11 +151,13 @@ class GraphedDetector:
         out = {"pred_logits": real_rows(plan.logits, 1), "pred_boxes": real_rows(plan.out_boxes, 1),
                "hs_embed": real_rows(plan.hs_embed, 1)}
         features = plan.features
-        if self.multi_frame and plan.graph is not None:
+        if self.uses_prev and plan.graph is not None:
             # the static feature maps are overwritten by the next replay, but the tracker hands them back as
             # prev_features (possibly several frames later, prev_frame_dist > 1): give it its own copy
             features = []
             for f in plan.features:
                 mask = f.mask
                 features.append(NestedTensor(f.tensors.clone(), mask))
+        # NB: for models that never read prev_features the returned `features` / `memory` (and, when no filler rows had
+        # to be dropped, the output rows) are views of the graph's static buffers: valid until the next call.
         return out, targets, features, plan.memory, real_rows(plan.hs_all, 2)
