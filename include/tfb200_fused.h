@@ -108,6 +108,22 @@ int tfb200_frozen_bn_act_fwd_f32(const float* x, const float* residual, const fl
 int tfb200_frozen_bn_act_bwd_f32(const float* dy, const float* y, const float* scale, float* dx, float* dresidual,
                                  int64_t pixels, int C, int relu, void* stream);
 
+/* y[M][N] = act(x[M][K] . w[N][K]^T + bias[N])  -- the nn.Linear of the long-token projections / FFN
+ * (ops/modules/ms_deform_attn.py:64,69,70,88; models/deformable_transformer.py:282-286) as ONE hand-written
+ * tcgen05 kernel: TMA-staged 128x32 fp32 tiles, TF32 tensor-core products (tcgen05.mma kind::tf32), fp32
+ * accumulation in TMEM, bias (+ optional ReLU) in the epilogue, TMA store.  All row-major, contiguous, 16-byte aligned.
+ * Requires N % 128 == 0 and K % 32 == 0 (tfb200_tf32_linear_supported); M is arbitrary.  bias may be NULL.
+ * Returns -5 (unsupported) outside that domain: the caller keeps the library GEMM for those.                          */
+int tfb200_tf32_linear_supported(int64_t M, int N, int K);
+int tfb200_tf32_linear_f32(const float* x, const float* w, const float* bias, float* y, int64_t M, int N, int K,
+                           int relu, void* stream);
+/* The layer's two backward products on the same pipeline:
+ *   dx[M][K]  = dy[M][N] . w[N][K]            (N % 32 == 0, K % 128 == 0)
+ *   dw[N][K]  = dy[M][N]^T . x[M][K]          (N, K % 128 == 0; the token axis M is split over all SMs, the partial
+ *                                              products are added into dw by TMA reductions; dw is zero-filled here) */
+int tfb200_tf32_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, int N, int K, void* stream);
+int tfb200_tf32_linear_wgrad_f32(const float* dy, const float* x, float* dw, int64_t M, int N, int K, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

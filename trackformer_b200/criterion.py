@@ -104,7 +104,7 @@ class SetCriterion(nn.Module):
         assert loss in table, f"do you really want to compute {loss} loss?"
         return table[loss](outputs, targets, indices, num_boxes, **kwargs)
 
-    def forward(self, outputs, targets):
+    def forward(self, outputs, targets, num_boxes=None):
         last = {k: v for k, v in outputs.items() if k != "aux_outputs"}
         aux_list = list(outputs.get("aux_outputs", ()))
         if hasattr(self.matcher, "match_layers"):
@@ -114,7 +114,9 @@ class SetCriterion(nn.Module):
         indices = all_indices[0]
 
         n_boxes = sum(len(t["labels"]) for t in targets)
-        if is_dist_avail_and_initialized():
+        if num_boxes is not None:
+            pass                                # the caller already ran the (collective) normaliser for this step
+        elif is_dist_avail_and_initialized():
             t = torch.as_tensor([n_boxes], dtype=torch.float, device=next(iter(outputs.values())).device)
             torch.distributed.all_reduce(t)
             num_boxes = torch.clamp(t / get_world_size(), min=1).item()
@@ -142,6 +144,20 @@ class SetCriterion(nn.Module):
             return torch.clamp(t / get_world_size(), min=1).item()
         return float(max(n_boxes, 1))
 
+    def num_boxes_device(self, targets, device, out=None):
+        """The loss normaliser of detr.py:397-401 as a 0-dim DEVICE tensor: mean box count over the ranks, at least 1,
+        without reading anything back (one scalar all-reduce when several ranks run).  ``out`` receives the value in
+        place, so a captured step can read it from a static buffer."""
+        t = torch.tensor(float(sum(len(t["labels"]) for t in targets)), dtype=torch.float32).to(device, non_blocking=True)
+        if is_dist_avail_and_initialized():
+            torch.distributed.all_reduce(t)
+            t = t / get_world_size()
+        t = torch.clamp(t, min=1)
+        if out is not None:
+            out.copy_(t)
+            return out
+        return t
+
     def forward_stacked(self, logits, boxes, targets, num_boxes=None):
         """Same losses as ``forward`` for a detector whose K decoder layers arrive stacked --
         ``logits [K,B,Q,C]``, ``boxes [K,B,Q,4]``, last layer = final prediction -- computed in ONE pass over
@@ -156,7 +172,7 @@ class SetCriterion(nn.Module):
         if special or min(sizes) == 0 or max(sizes) > nq:
             out = dict(layers[-1])
             out["aux_outputs"] = layers[:-1]
-            return self.forward(out, targets)
+            return self.forward(out, targets, num_boxes)
 
         dev = logits.device
         per_layer = sum(sizes)

@@ -216,21 +216,32 @@ add_dropout_ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict_
 // out[c] = sum_b partial[b][c] for c < width, written to out0 (c < split) / out1 (c >= split).  One warp per 32
 // output columns: lane = column (coalesced 128-byte reads of each partial row), the 8 warps of a CTA split the partial
 // rows and combine through shared memory in a fixed order -> deterministic.
-__global__ void __launch_bounds__(256)
+constexpr int kFinishWarps = 32;
+__global__ void __launch_bounds__(kFinishWarps * 32)
 column_partials_finish_kernel(const float* __restrict__ partial, float* __restrict__ out0, float* __restrict__ out1,
                               int nblocks, int width, int split) {
-  __shared__ float acc_s[8][32];
+  // 8 CTAs x 8 warps walking 592 partial rows one dependent load at a time took ~9 us (latency-bound, 63 calls per
+  // step); 32 warps with four independent loads in flight each bring that to the launch floor.  Fixed order -> deterministic.
+  __shared__ float acc_s[kFinishWarps][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
-  float acc = 0.f;
-  if (c < width)
-    for (int b = w; b < nblocks; b += 8) acc += partial[size_t(b) * width + c];
-  acc_s[w][lane] = acc;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (c < width) {
+    int b = w;
+    for (; b + 3 * kFinishWarps < nblocks; b += 4 * kFinishWarps) {
+      a0 += partial[size_t(b) * width + c];
+      a1 += partial[size_t(b + kFinishWarps) * width + c];
+      a2 += partial[size_t(b + 2 * kFinishWarps) * width + c];
+      a3 += partial[size_t(b + 3 * kFinishWarps) * width + c];
+    }
+    for (; b < nblocks; b += kFinishWarps) a0 += partial[size_t(b) * width + c];
+  }
+  acc_s[w][lane] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (w == 0 && c < width) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += acc_s[k][lane];
+    for (int k = 0; k < kFinishWarps; ++k) t += acc_s[k][lane];
     if (c < split) out0[c] = t; else out1[c - split] = t;
   }
 }
@@ -371,7 +382,7 @@ static int ln_backward(const float* dy, const float* s, const uint8_t* keep_mask
     default: return TFB200_E_SHAPE;   // the 48 KB static shared-memory reduction buffer bounds C at 512 here
   }
 #undef TFB200_BWD
-  column_partials_finish_kernel<<<(2 * C + 31) / 32, 256, 0, st>>>(partial_ws, dgamma, dbeta, grid, 2 * C, C);
+  column_partials_finish_kernel<<<(2 * C + 31) / 32, kFinishWarps * 32, 0, st>>>(partial_ws, dgamma, dbeta, grid, 2 * C, C);
   msda_b200_count_launches(2);
   return int(cudaGetLastError());
 }
@@ -427,7 +438,7 @@ int tfb200_colsum_f32(const float* x, float* out, float* partial_ws, int64_t row
     default: return TFB200_E_SHAPE;
   }
 #undef TFB200_CS
-  column_partials_finish_kernel<<<(C + 31) / 32, 256, 0, st>>>(partial_ws, out, out, grid, C, C);
+  column_partials_finish_kernel<<<(C + 31) / 32, kFinishWarps * 32, 0, st>>>(partial_ws, out, out, grid, C, C);
   msda_b200_count_launches(2);
   return int(cudaGetLastError());
 }

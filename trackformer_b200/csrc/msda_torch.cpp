@@ -222,6 +222,65 @@ at::Tensor colsum(const at::Tensor& x) {
   return out;
 }
 
+// y = act(x . w^T + bias) on the hand-written tcgen05 TF32 kernel (csrc/tf32_gemm.cu); x [..., K], w [N, K], bias [N] or None
+bool tf32_linear_supported(int64_t rows, int64_t n, int64_t k) { return tfb200_tf32_linear_supported(rows, int(n), int(k)) != 0; }
+
+at::Tensor tf32_linear(const at::Tensor& x, const at::Tensor& w, const c10::optional<at::Tensor>& bias, bool relu) {
+  TORCH_CHECK(x.is_cuda() && w.is_cuda() && x.scalar_type() == at::kFloat && w.scalar_type() == at::kFloat && w.dim() == 2,
+              "tf32_linear: fp32 CUDA tensors required");
+  const int64_t K = w.size(1), N = w.size(0);
+  TORCH_CHECK(x.dim() >= 1 && x.size(-1) == K, "tf32_linear: x[..., K] against w[N, K]");
+  const at::Tensor xc = x.contiguous(), wc = w.contiguous();
+  const int64_t M = xc.numel() / K;
+  const float* bp = nullptr;
+  at::Tensor bc;
+  if (bias.has_value() && bias->defined()) {
+    TORCH_CHECK(bias->is_cuda() && bias->scalar_type() == at::kFloat && bias->numel() == N, "tf32_linear: bias[N]");
+    bc = bias->contiguous();
+    bp = bc.data_ptr<float>();
+  }
+  const c10::cuda::CUDAGuard guard(x.device());
+  auto sizes = xc.sizes().vec();
+  sizes.back() = N;
+  at::Tensor y = at::empty(sizes, xc.options());
+  if (M == 0) return y;
+  const int rc = tfb200_tf32_linear_f32(xc.data_ptr<float>(), wc.data_ptr<float>(), bp, y.data_ptr<float>(), M, int(N),
+                                        int(K), relu ? 1 : 0, c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "tf32_linear failed (code ", rc, "): needs N % 128 == 0, K % 32 == 0, 16-byte aligned operands");
+  return y;
+}
+
+// dx = dy . w  and  dw = dy^T . x  of the same layer (csrc/tf32_gemm.cu, modes dgrad / wgrad)
+at::Tensor tf32_linear_dgrad(const at::Tensor& dy, const at::Tensor& w) {
+  TORCH_CHECK(dy.is_cuda() && w.is_cuda() && dy.scalar_type() == at::kFloat && w.scalar_type() == at::kFloat && w.dim() == 2 &&
+              dy.size(-1) == w.size(0), "tf32_linear_dgrad: dy[..., N] against w[N, K]");
+  const at::Tensor g = dy.contiguous(), wc = w.contiguous();
+  const int64_t N = wc.size(0), K = wc.size(1), M = g.numel() / N;
+  const c10::cuda::CUDAGuard guard(dy.device());
+  auto sizes = g.sizes().vec();
+  sizes.back() = K;
+  at::Tensor dx = at::empty(sizes, g.options());
+  if (M == 0) return dx;
+  const int rc = tfb200_tf32_linear_dgrad_f32(g.data_ptr<float>(), wc.data_ptr<float>(), dx.data_ptr<float>(), M, int(N),
+                                              int(K), c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "tf32_linear_dgrad failed (code ", rc, ")");
+  return dx;
+}
+
+at::Tensor tf32_linear_wgrad(const at::Tensor& dy, const at::Tensor& x) {
+  TORCH_CHECK(dy.is_cuda() && x.is_cuda() && dy.scalar_type() == at::kFloat && x.scalar_type() == at::kFloat,
+              "tf32_linear_wgrad: fp32 CUDA tensors required");
+  const at::Tensor g = dy.contiguous(), xc = x.contiguous();
+  const int64_t N = g.size(-1), K = xc.size(-1), M = g.numel() / N;
+  TORCH_CHECK(xc.numel() / K == M, "tf32_linear_wgrad: dy[M, N] and x[M, K] must agree on M");
+  const c10::cuda::CUDAGuard guard(dy.device());
+  at::Tensor dw = at::empty({N, K}, g.options());
+  const int rc = tfb200_tf32_linear_wgrad_f32(g.data_ptr<float>(), xc.data_ptr<float>(), dw.data_ptr<float>(), M, int(N),
+                                              int(K), c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "tf32_linear_wgrad failed (code ", rc, ")");
+  return dw;
+}
+
 at::Tensor relu_dropout_forward(const at::Tensor& a, const c10::optional<at::Tensor>& seed, double keep_prob, bool training) {
   TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kFloat, "relu_dropout: fp32 CUDA tensor required");
   const at::Tensor ac = a.contiguous();
@@ -440,6 +499,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lsa", &lsa);
   m.def("sampling_prep_forward", &sampling_prep_forward);
   m.def("sampling_prep_backward", &sampling_prep_backward);
+  m.def("tf32_linear", &tf32_linear);
+  m.def("tf32_linear_supported", &tf32_linear_supported);
+  m.def("tf32_linear_dgrad", &tf32_linear_dgrad);
+  m.def("tf32_linear_wgrad", &tf32_linear_wgrad);
   m.def("relu_dropout_forward", &relu_dropout_forward);
   m.def("relu_dropout_backward", &relu_dropout_backward);
   m.def("detect_postprocess", &detect_postprocess);

@@ -52,10 +52,29 @@ def weight_grad(gy2: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
     return gw
 
 
+# Forward products of the long-token Linears on the hand-written tcgen05 kernel (csrc/tf32_gemm.cu) whenever TF32
+# tensor-core math is allowed (torch.backends.cuda.matmul.allow_tf32 -- the benchmark setting; strict-fp32 runs keep the
+# library's fp32 GEMM).  TFB200_TCGEN05_LINEAR=0 switches it off (A/B timing).
+_TCGEN05 = os.environ.get("TFB200_TCGEN05_LINEAR", "1") != "0"
+
+
+# Which of the three products run on it: "fdw" = forward, dgrad, wgrad (default all three).
+_TCGEN05_PARTS = os.environ.get("TFB200_TCGEN05_PARTS", "fdw")
+
+
+def _tcgen05_ok(x, weight):
+    if not (_TCGEN05 and torch.backends.cuda.matmul.allow_tf32 and x.is_contiguous() and weight.is_contiguous()):
+        return False
+    return bool(ext.load().tf32_linear_supported(x.numel() // x.shape[-1], weight.shape[0], weight.shape[1]))
+
+
 class _LinearColsum(Function):
     @staticmethod
     def forward(ctx, x, weight, bias):
         ctx.save_for_backward(x, weight)
+        ctx.tc = _tcgen05_ok(x, weight)
+        if ctx.tc and "f" in _TCGEN05_PARTS:
+            return ext.load().tf32_linear(x, weight, bias, False)
         return F.linear(x, weight, bias)
 
     @staticmethod
@@ -64,10 +83,17 @@ class _LinearColsum(Function):
         x, weight = ctx.saved_tensors
         gy2 = gy.reshape(-1, gy.shape[-1])
         gx = gw = gb = None
+        m = ext.load()
         if ctx.needs_input_grad[0]:
-            gx = (gy2 @ weight).view(x.shape)
+            if ctx.tc and "d" in _TCGEN05_PARTS and gy2.is_contiguous():
+                gx = m.tf32_linear_dgrad(gy2, weight).view(x.shape)
+            else:
+                gx = (gy2 @ weight).view(x.shape)
         if ctx.needs_input_grad[1]:
-            gw = weight_grad(gy2, x.reshape(-1, x.shape[-1]))
+            if ctx.tc and "w" in _TCGEN05_PARTS and gy2.is_contiguous():
+                gw = m.tf32_linear_wgrad(gy2, x.reshape(-1, x.shape[-1]))
+            else:
+                gw = weight_grad(gy2, x.reshape(-1, x.shape[-1]))
         if ctx.needs_input_grad[2]:
             gb = ext.load().colsum(gy2)
         return gx, gw, gb

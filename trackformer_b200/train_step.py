@@ -65,9 +65,10 @@ class TrainStep:
             prepare()                                   # final parameter memory formats before gradient views exist
         self.params: List[nn.Parameter] = [p for p in model.parameters() if p.requires_grad]
         self.core = _DetectorCore(model)
-        # with several ranks the loss normaliser is the world-averaged box count: the full-step graph bakes it in, which
-        # is only valid while every rank keeps its box counts (the benchmark does); variable data uses the two-graph path
-        self._static_world_boxes = True
+        # The loss normaliser (world-averaged box count, detr.py:397-401) is a device scalar in a static buffer, refreshed
+        # every step by ONE scalar all-reduce that every rank issues on every path -- so ranks may take different
+        # paths (full-step graph / two graphs / eager) in the same step and still run the same collective sequence.
+        self.s_num_boxes = None
         self.g_fwd = self.g_bwd = self.g_full = None
         # gradient hand-over instead of per-parameter accumulation (see _backward_into_flat)
         self.gather_grads = os.environ.get("TFB200_GATHER_GRADS", "1") != "0"
@@ -157,11 +158,12 @@ class TrainStep:
         ground truth has the captured per-image box counts (boxes / labels are copied into static buffers).  Other
         box counts take the two-graph path with the loss in between."""
         self.full_sizes = tuple(len(t["labels"]) for t in example_targets)
-        if min(self.full_sizes) == 0:
+        if min(self.full_sizes) == 0:                      # (no collective before this point: ranks may differ here)
             return
         self.s_targets = [{"boxes": t["boxes"].clone(), "labels": t["labels"].clone()} for t in example_targets]
         dev = self.static_frames.device
-        self.s_num_boxes = self.criterion._num_boxes(self.s_targets, dev)      # static normaliser (may sync once)
+        # local count for the warm-up / capture passes; __call__ overwrites it with the world average every step
+        self.s_num_boxes = torch.tensor(float(max(sum(self.full_sizes), 1)), device=dev)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                                            # memos, lazy inits
@@ -212,9 +214,19 @@ class TrainStep:
         wd = self.criterion.weight_dict
         return sum(loss_dict[k] * wd[k] for k in loss_dict if k in wd)
 
+    def _normaliser(self, targets, device):
+        if self.s_num_boxes is None:
+            self.s_num_boxes = torch.ones((), device=device)
+        if hasattr(self.criterion, "num_boxes_device"):
+            return self.criterion.num_boxes_device(targets, device, out=self.s_num_boxes)
+        return None
+
     def __call__(self, frames: torch.Tensor, targets: list) -> torch.Tensor:
-        if self.g_full is not None and tuple(len(t["labels"]) for t in targets) == self.full_sizes \
-                and (self.world == 1 or self._static_world_boxes):
+        dev = self.flat_grad.device
+        full = self.g_full is not None and tuple(len(t["labels"]) for t in targets) == self.full_sizes
+        # one scalar all-reduce per step on EVERY path, before anything else (same collective order on all ranks)
+        num_boxes = self._normaliser(targets, dev) if (self.world > 1 or full) else None
+        if full:
             if frames is not self.static_frames:
                 self.static_frames.copy_(frames, non_blocking=True)     # device or pinned-host source
             for st, t in zip(self.s_targets, targets):
@@ -229,14 +241,14 @@ class TrainStep:
             self.g_fwd.replay()
             logits = self.s_logits.detach().requires_grad_(True)
             boxes = self.s_boxes.detach().requires_grad_(True)
-            loss = self._loss(logits, boxes, targets)
+            loss = self._loss(logits, boxes, targets, num_boxes)
             g_logits, g_boxes = torch.autograd.grad(loss, (logits, boxes))
             self.s_glogits.copy_(g_logits)
             self.s_gboxes.copy_(g_boxes)
             self.g_bwd.replay()
         else:
             logits, boxes = self.core(frames)
-            loss = self._loss(logits, boxes, targets)
+            loss = self._loss(logits, boxes, targets, num_boxes)
             self._backward_into_flat(loss)
         if self.world > 1:
             dist.all_reduce(self.flat_grad)
