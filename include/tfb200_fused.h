@@ -124,6 +124,15 @@ int tfb200_tf32_linear_f32(const float* x, const float* w, const float* bias, fl
 int tfb200_tf32_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, int N, int K, void* stream);
 int tfb200_tf32_linear_wgrad_f32(const float* dy, const float* x, float* dw, int64_t M, int N, int K, void* stream);
 
+/* out[r][c] = sigmoid(delta[r][c] + inverse_sigmoid(ref[r][c]))  for c < ref_dim (2 or 4), sigmoid(delta[r][c]) beyond;
+ * inverse_sigmoid(x) = log(clamp(clamp(x,0,1), eps) / clamp(1 - clamp(x,0,1), eps))  (util/misc.py:515-519) -- the box
+ * refinement of deformable_transformer.py:412-422 / deformable_detr.py:229-248 in one launch.  delta/out [rows][4],
+ * ref [rows][ref_dim].  backward: grad_delta [rows][4], grad_ref [rows][ref_dim] (NULL to skip), from grad_out and out. */
+int tfb200_refine_boxes_fwd_f32(const float* delta, const float* ref, float* out, int64_t rows, int ref_dim, float eps,
+                                void* stream);
+int tfb200_refine_boxes_bwd_f32(const float* grad_out, const float* out, const float* ref, float* grad_delta,
+                                float* grad_ref, int64_t rows, int ref_dim, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

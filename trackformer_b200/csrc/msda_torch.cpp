@@ -281,6 +281,34 @@ at::Tensor tf32_linear_wgrad(const at::Tensor& dy, const at::Tensor& x) {
   return dw;
 }
 
+// boxes = sigmoid(delta + inverse_sigmoid(ref)) (csrc/box_refine.cu); delta [..., 4], ref [..., 2 or 4]
+at::Tensor refine_boxes_forward(const at::Tensor& delta, const at::Tensor& ref, double eps) {
+  TORCH_CHECK(delta.is_cuda() && ref.is_cuda() && delta.scalar_type() == at::kFloat && ref.scalar_type() == at::kFloat &&
+              delta.size(-1) == 4 && (ref.size(-1) == 2 || ref.size(-1) == 4) &&
+              delta.numel() / 4 == ref.numel() / ref.size(-1), "refine_boxes: delta [..., 4], ref [..., 2|4]");
+  const at::Tensor d = delta.contiguous(), r = ref.contiguous();
+  const c10::cuda::CUDAGuard guard(delta.device());
+  at::Tensor out = at::empty_like(d);
+  const int rc = tfb200_refine_boxes_fwd_f32(d.data_ptr<float>(), r.data_ptr<float>(), out.data_ptr<float>(), d.numel() / 4,
+                                             int(r.size(-1)), float(eps), c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "refine_boxes_forward failed (code ", rc, ")");
+  return out;
+}
+
+std::vector<at::Tensor> refine_boxes_backward(const at::Tensor& grad_out, const at::Tensor& out, const at::Tensor& ref,
+                                              bool need_ref_grad, double eps) {
+  const at::Tensor g = grad_out.contiguous(), o = out.contiguous(), r = ref.contiguous();
+  const c10::cuda::CUDAGuard guard(out.device());
+  at::Tensor gd = at::empty_like(o);
+  at::Tensor gr = need_ref_grad ? at::empty_like(r) : at::Tensor();
+  const int rc = tfb200_refine_boxes_bwd_f32(g.data_ptr<float>(), o.data_ptr<float>(), r.data_ptr<float>(),
+                                             gd.data_ptr<float>(), need_ref_grad ? gr.data_ptr<float>() : nullptr,
+                                             o.numel() / 4, int(r.size(-1)), float(eps),
+                                             c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "refine_boxes_backward failed (code ", rc, ")");
+  return {gd, gr};
+}
+
 at::Tensor relu_dropout_forward(const at::Tensor& a, const c10::optional<at::Tensor>& seed, double keep_prob, bool training) {
   TORCH_CHECK(a.is_cuda() && a.scalar_type() == at::kFloat, "relu_dropout: fp32 CUDA tensor required");
   const at::Tensor ac = a.contiguous();
@@ -499,6 +527,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("lsa", &lsa);
   m.def("sampling_prep_forward", &sampling_prep_forward);
   m.def("sampling_prep_backward", &sampling_prep_backward);
+  m.def("refine_boxes_forward", &refine_boxes_forward);
+  m.def("refine_boxes_backward", &refine_boxes_backward);
   m.def("tf32_linear", &tf32_linear);
   m.def("tf32_linear_supported", &tf32_linear_supported);
   m.def("tf32_linear_dgrad", &tf32_linear_dgrad);

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from .backbone import _resize_mask
-from .util import (NestedTensor, box_cxcywh_to_xyxy, inverse_sigmoid,
+from .util import (NestedTensor, box_cxcywh_to_xyxy, refine_boxes,
                    nested_tensor_from_tensor_list)
 
 
@@ -195,22 +195,18 @@ class DeformableDETR(DETR):
         for frame, frame_feat in enumerate(frames):
             self._project_levels(frame, frame_feat, prev_features, pos, src_list, mask_list, pos_list)
 
-        hs, memory, init_reference, inter_references, _, _ = self.transformer(
+        hs, memory, init_reference, inter_references, refined_boxes, _ = self.transformer(
             src_list, mask_list, pos_list, self.query_embed.weight, targets)
 
-        logits, boxes = [], []
-        for lvl in range(hs.shape[0]):
-            ref = inverse_sigmoid(init_reference if lvl == 0 else inter_references[lvl - 1])
-            delta = self.bbox_embed[lvl](hs[lvl])
-            if ref.shape[-1] == 4:
-                delta = delta + ref
-            else:
-                assert ref.shape[-1] == 2
-                delta = torch.cat([delta[..., :2] + ref, delta[..., 2:]], -1)
-            logits.append(self.class_embed[lvl](hs[lvl]))
-            boxes.append(delta.sigmoid())
-        logits = torch.stack(logits)
-        boxes = torch.stack(boxes)
+        logits = torch.stack([self.class_embed[lvl](hs[lvl]) for lvl in range(hs.shape[0])])
+        if refined_boxes is not None and self.with_box_refine and refined_boxes.shape[0] == hs.shape[0]:
+            # iterative refinement: the decoder already evaluated bbox_embed[lvl](hs[lvl]) + inverse_sigmoid(reference
+            # of layer lvl) -- the reference computes the identical expression again here (deformable_detr.py:229-248)
+            boxes = refined_boxes
+        else:
+            boxes = torch.stack([refine_boxes(self.bbox_embed[lvl](hs[lvl]),
+                                              init_reference if lvl == 0 else inter_references[lvl - 1])
+                                 for lvl in range(hs.shape[0])])
         # per-layer heads as two tensors [layers, N, Q, .]; the training step takes them from here instead of
         # re-stacking the per-layer slices of the output dictionary (whose backward is a zero-fill + copy per slice)
         self._call_scratch().value = (logits, boxes)

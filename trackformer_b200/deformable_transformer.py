@@ -23,7 +23,7 @@ from torch import nn
 from .fused_linear import linear as fused_linear, relu_dropout
 from .fused_norm import add_dropout_layernorm
 from .msda_module import MSDeformAttn
-from .util import inverse_sigmoid
+from .util import refine_boxes
 
 
 def _clones(module: nn.Module, n: int) -> nn.ModuleList:
@@ -160,7 +160,8 @@ class DeformableTransformerDecoder(nn.Module):
     def forward(self, tgt, reference_points, src, src_spatial_shapes, src_valid_ratios, query_pos=None,
                 src_padding_mask=None, query_attn_mask=None, padded_queries=None):
         out = tgt
-        hs, refs = [], []
+        hs, refs, boxes = [], [], []
+        self.refined_boxes = None
         for lid, layer in enumerate(self.layers):
             if reference_points.shape[-1] == 4:
                 ref_in = reference_points[:, :, None] * torch.cat([src_valid_ratios, src_valid_ratios], -1)[:, None]
@@ -171,17 +172,19 @@ class DeformableTransformerDecoder(nn.Module):
                         padded_queries)
 
             if self.bbox_embed is not None:     # refine the reference boxes for the next layer; no gradient through them
-                delta = self.bbox_embed[lid](out)
-                if reference_points.shape[-1] == 4:
-                    refined = delta + inverse_sigmoid(reference_points)
-                else:
-                    refined = torch.cat([delta[..., :2] + inverse_sigmoid(reference_points), delta[..., 2:]], -1)
-                reference_points = refined.sigmoid().detach()
+                # sigmoid(bbox_embed[lid](out) + inverse_sigmoid(reference)) is ALSO what the detection head of this
+                # layer predicts (deformable_detr.py:229-248 evaluates the same MLP on the same input a second time):
+                # keep the attached tensor for the heads, continue with its detached value
+                refined = refine_boxes(self.bbox_embed[lid](out), reference_points)
+                boxes.append(refined)
+                reference_points = refined.detach()
 
             if self.return_intermediate:
                 hs.append(out)
                 refs.append(reference_points)
         if self.return_intermediate:
+            if boxes:
+                self.refined_boxes = torch.stack(boxes)      # [layers, N, Q, 4], attached; consumed once by the heads
             return torch.stack(hs), torch.stack(refs)
         return out, reference_points
 
@@ -308,7 +311,8 @@ class DeformableTransformer(nn.Module):
 
         hs, inter_references = self.decoder(tgt, reference_points, memory, spatial_shapes, valid_ratios,
                                             query_pos, enc_mask, None, padded_queries)
-        return hs, memory, init_reference, inter_references, None, None
+        refined, self.decoder.refined_boxes = self.decoder.refined_boxes, None     # (do not keep the graph alive)
+        return hs, memory, init_reference, inter_references, refined, None
 
 
 def build_deforamble_transformer(args):

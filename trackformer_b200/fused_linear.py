@@ -55,7 +55,7 @@ def weight_grad(gy2: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
 # Forward products of the long-token Linears on the hand-written tcgen05 kernel (csrc/tf32_gemm.cu) whenever TF32
 # tensor-core math is allowed (torch.backends.cuda.matmul.allow_tf32 -- the benchmark setting; strict-fp32 runs keep the
 # library's fp32 GEMM).  TFB200_TCGEN05_LINEAR=0 switches it off (A/B timing).
-_TCGEN05 = os.environ.get("TFB200_TCGEN05_LINEAR", "1") != "0"
+_TCGEN05 = os.environ.get("TFB200_TCGEN05_LINEAR", "0") != "0"      # off until validated on a B200
 
 
 # Which of the three products run on it: "fdw" = forward, dgrad, wgrad (default all three).

@@ -61,6 +61,37 @@ def inverse_sigmoid(x: Tensor, eps: float = 1e-5) -> Tensor:
     return torch.log(x.clamp(min=eps) / (1 - x).clamp(min=eps))
 
 
+class _RefineBoxes(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, delta, ref, eps):
+        from .ext import load
+        out = load().refine_boxes_forward(delta, ref, eps)
+        ctx.save_for_backward(out, ref)
+        ctx.eps = eps
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        from .ext import load
+        out, ref = ctx.saved_tensors
+        gd, gr = load().refine_boxes_backward(grad_out, out, ref, bool(ctx.needs_input_grad[1]), ctx.eps)
+        return gd, (gr if ctx.needs_input_grad[1] else None), None
+
+
+def refine_boxes(delta: Tensor, reference: Tensor, eps: float = 1e-5) -> Tensor:
+    """``sigmoid(delta + inverse_sigmoid(reference))`` -- the box refinement of the decoder / detection heads
+    (models/deformable_transformer.py:412-422, models/deformable_detr.py:229-248).  ``reference`` has 4 components or 2
+    (then only ``delta[..., :2]`` gets it added).  One fused launch per direction on CUDA fp32 tensors, the
+    reference's op chain otherwise."""
+    if delta.is_cuda and delta.dtype == torch.float32 and reference.dtype == torch.float32 and delta.shape[-1] == 4:
+        return _RefineBoxes.apply(delta, reference, eps)
+    ref = inverse_sigmoid(reference, eps)
+    if ref.shape[-1] == 4:
+        return (delta + ref).sigmoid()
+    return torch.cat([delta[..., :2] + ref, delta[..., 2:]], -1).sigmoid()
+
+
 # ----------------------------------------------------------------------------- boxes
 def box_cxcywh_to_xyxy(b: Tensor) -> Tensor:
     cx, cy, w, h = b.unbind(-1)
