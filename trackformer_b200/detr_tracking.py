@@ -12,8 +12,8 @@ from the CPU torch generator in ``add_track_queries_to_targets``:
   4. randperm(kept)[:n_fp]                           which survivors spawn a false positive    (:104)
   5. multinomial(weights, 1) | randperm(n_unmatched)[0]   which unmatched query becomes it     (:137,:139)
 
-tests/test_tracking_bookkeeping.py checks the resulting index tensors bit-for-bit against fixtures produced
-by the reference class.  The reference's distance weight uses the x-offset twice (:131) -- kept, since it
+tests/test_model_parity_cpu.py::test_add_track_queries_bit_exact_against_reference (and the tracking train-step tests on
+CPU and GPU) check the resulting index tensors bit-for-bit against fixtures produced by the reference class.  The reference's distance weight uses the x-offset twice (:131) -- kept, since it
 changes which index the multinomial draws.
 """
 from __future__ import annotations
@@ -51,8 +51,17 @@ class DETRTrackingBase(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def add_track_queries_to_targets(self, targets, prev_indices, prev_out, add_false_pos=True):
+        """Host-side bookkeeping with ONE device->host transfer.
+
+        The reference interleaves the index logic with device reads: a ``.tolist()`` per sample, a ``weights.cpu()`` per
+        injected false positive, ``nonzero`` on device tensors (detr_tracking.py:39-217) -- a dozen synchronisations per
+        training step.  Here the previous frame's boxes (and the few identity vectors, if they live on the device) come to
+        the host once, every decision is taken there with the same arithmetic (fp32 subtract / square / add / sqrt are
+        exactly rounded on both sides) and the same five draws from the CPU generator in the same order, and the results
+        go back as index tensors: the embeddings / boxes are gathered on the device with one index each."""
         device = prev_out["pred_boxes"].device
         n_queries_prev = prev_out["pred_boxes"].shape[1]
+        boxes_host = prev_out["pred_boxes"].detach().to("cpu")                   # the one device->host transfer
 
         fewest = min(len(tgt_i) for _, tgt_i in prev_indices)
         n_keep = torch.randint(0, fewest + 1, (1,)).item() if fewest else 0                            # draw 1
@@ -61,42 +70,41 @@ class DETRTrackingBase(nn.Module):
             n_fp = torch.randint(int(math.ceil(self._track_query_false_positive_prob * n_keep)) + 1, (1,)).item()  # draw 2
 
         for i, (target, (out_i, tgt_i)) in enumerate(zip(targets, prev_indices)):
+            out_i, tgt_i = out_i.to("cpu"), tgt_i.to("cpu")
             if self._track_query_false_negative_prob:
                 keep = torch.randperm(len(tgt_i))[:n_keep]                                             # draw 3
                 out_i, tgt_i = out_i[keep], tgt_i[keep]
 
             # identities seen in the previous frame that are still present in the current one
-            prev_ids = target["prev_target"]["track_ids"][tgt_i]
-            same_id = prev_ids.unsqueeze(1).eq(target["track_ids"])
+            prev_ids = target["prev_target"]["track_ids"].to("cpu")[tgt_i]
+            same_id = prev_ids.unsqueeze(1).eq(target["track_ids"].to("cpu"))
             still_there = same_id.any(dim=1)
-            target["track_query_match_ids"] = same_id.nonzero()[:, 1]
+            match_ids = same_id.nonzero()[:, 1]
 
             if add_false_pos:
-                matched_boxes = prev_out["pred_boxes"][i, out_i[still_there.to(out_i.device)]]
+                matched_xy = boxes_host[i, out_i[still_there]][:, :2]
                 taken = set(out_i.tolist())
                 free = [q for q in range(n_queries_prev) if q not in taken]
+                free_xy = boxes_host[i, :, :2]
                 injected = []
                 for j in torch.randperm(n_keep)[:n_fp]:                                                # draw 4
-                    free_boxes = prev_out["pred_boxes"][i, free]
-                    if len(matched_boxes) > j:
-                        dx = matched_boxes[j].unsqueeze(0)[:, :2] - free_boxes[:, :2]
+                    if len(matched_xy) > j:
+                        dx = matched_xy[j].unsqueeze(0) - free_xy[free]
                         weights = torch.sqrt(dx[:, 0] ** 2 + dx[:, 0] ** 2)                            # (sic) x twice
-                        pick = torch.multinomial(weights.cpu(), 1).item()                              # draw 5a
+                        pick = torch.multinomial(weights, 1).item()                                    # draw 5a
                     else:
                         pick = torch.randperm(len(free))[0]                                            # draw 5b
                     injected.append(free.pop(pick))
                 out_i = torch.tensor(out_i.tolist() + injected).long()
-                still_there = torch.cat([still_there, torch.tensor([False] * len(injected)).bool().to(device)])
+                still_there = torch.cat([still_there, torch.zeros(len(injected), dtype=torch.bool)])
 
-            is_track = torch.ones_like(still_there).bool()
-            is_false_pos = torch.zeros_like(still_there).bool()
-            is_false_pos[~still_there] = True
-
-            target["track_query_hs_embeds"] = prev_out["hs_embed"][i, out_i]
-            target["track_query_boxes"] = prev_out["pred_boxes"][i, out_i].detach()
-            pad = torch.tensor([False] * self.num_queries).to(device)
-            target["track_queries_mask"] = torch.cat([is_track, pad]).bool()
-            target["track_queries_fal_pos_mask"] = torch.cat([is_false_pos, pad]).bool()
+            pad = torch.zeros(self.num_queries, dtype=torch.bool)
+            rows = out_i.to(device)
+            target["track_query_match_ids"] = match_ids.to(device)
+            target["track_query_hs_embeds"] = prev_out["hs_embed"][i].index_select(0, rows)
+            target["track_query_boxes"] = prev_out["pred_boxes"][i].index_select(0, rows).detach()
+            target["track_queries_mask"] = torch.cat([torch.ones_like(still_there), pad]).to(device)
+            target["track_queries_fal_pos_mask"] = torch.cat([~still_there, pad]).to(device)
 
     # ------------------------------------------------------------------------------------------
     def forward(self, samples: NestedTensor, targets: list = None, prev_features=None):
