@@ -56,6 +56,7 @@ def _worker(rank, world, port, out_dir):
         model, criterion = _build_small()
         step = TrainStep(model, criterion, None, use_graphs=False)
         assert step.world == world
+        assert step.phased            # three-piece backward, one all-reduce per finished gradient slice
         frames, targets = _data(rank)
         loss = step(frames, targets)
         torch.save({"grad": step.flat_grad.clone(), "loss": loss}, os.path.join(out_dir, f"rank{rank}.pt"))

@@ -21,7 +21,12 @@ def test_flat_layout_keeps_the_model_and_partitions_groups(oracle_op):
     assert sum(p.numel() for g in groups for p in g["params"]) == n_trainable
     step = TrainStep(model, criterion, None, use_graphs=False, flat_adamw={"groups": groups})
     ranges = step.flat_optimizer.ranges
-    assert all(e - b >= sum(p.numel() for p in g["params"]) for (b, e), g in zip(ranges, groups))
+    # (TrainStep moves the backbone group to the end of the buffers: ranges follow the optimizer's own group order)
+    placed = step.flat_optimizer.param_groups
+    assert sorted(id(p) for g in placed for p in g["params"]) == sorted(id(p) for g in groups for p in g["params"])
+    assert all(e - b >= sum(p.numel() for p in g["params"]) for (b, e), g in zip(ranges, placed))
+    names = {id(p): n for n, p in model.named_parameters()}
+    assert all(names[id(p)].startswith("backbone.") for p in placed[-1]["params"])
     assert all(b % 64 == 0 for b, _ in ranges) and all((p.data_ptr() - step.flat_param.data_ptr()) % 256 == 0 and (p.grad.data_ptr() - step.flat_grad.data_ptr()) % 256 == 0 for p in step.params)
     assert all(b % 4 == 0 for b, _ in ranges) and all(ranges[i][1] <= ranges[i + 1][0] for i in range(len(ranges) - 1))
     lo, hi = step.flat_param.data_ptr(), step.flat_param.data_ptr() + 4 * step.flat_param.numel()

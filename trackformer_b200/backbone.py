@@ -95,9 +95,15 @@ class _Trunk(nn.ModuleDict):
         super().__init__({name: mod for i, (name, mod) in enumerate(resnet.named_children()) if i <= last})
         self.taps = dict(taps)
 
+    #: optional ``cut(tag, tensor) -> tensor`` installed by TrainStep's phased backward: called on every tapped stage
+    #: output and on the tensor handed from layer3 to layer4, it may return a detached leaf so that the backward can be
+    #: run (and its gradients all-reduced) in pieces.  None = plain forward.
+    cut = None
+
     def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
         collected = {}
         fuse_stem = getattr(self, "fused_bn", False)
+        cut = self.cut
         for name, stage in self.items():
             if fuse_stem and name == "bn1":
                 from .fused_bn import bn_act
@@ -108,7 +114,9 @@ class _Trunk(nn.ModuleDict):
             x = stage(x)
             key = self.taps.get(name)
             if key is not None:
-                collected[key] = x
+                collected[key] = x if cut is None else cut(name + "/tap", x)
+            if cut is not None and name == "layer3":
+                x = cut("layer3/next", x)
         return collected
 
 

@@ -75,13 +75,20 @@ class TrainStep:
 
         # flat layout: groups (if any) are contiguous and start on a 16-byte boundary
         groups = None
+        names = {id(p): n for n, p in model.named_parameters()}
+        is_bb = lambda p: names.get(id(p), "").startswith("backbone.")                       # noqa: E731
         if flat_adamw is not None:
             assert optimizer_factory is None, "give either optimizer_factory or flat_adamw"
             groups = [dict(g, params=list(g["params"])) for g in flat_adamw["groups"]]
+            # groups made of backbone parameters go last: the flat buffers then read [transformer | backbone], the
+            # order in which the backward finishes them (see _phases)
+            groups.sort(key=lambda g: bool(g["params"]) and all(is_bb(p) for p in g["params"]))
             ordered = [p for g in groups for p in g["params"]]
             assert len({id(p) for p in ordered}) == len(ordered) == len(self.params) and \
                 {id(p) for p in ordered} == {id(p) for p in self.params}, "groups must partition the trainable parameters"
             self.params = ordered
+        else:
+            self.params.sort(key=is_bb)                                                      # stable: model order kept
         # every tensor starts on a 256-byte boundary: library GEMM / convolution kernels and the vectorised elementwise
         # kernels need 16-byte aligned operands, and a densely packed buffer would misalign everything behind the first
         # odd-sized bias (the padding -- < 64 floats per tensor -- stays zero in gradients, parameters and moments)
@@ -96,6 +103,21 @@ class TrainStep:
             ranges.append((begin, ofs))
         total = -(-ofs // align) * align
         dev = self.params[0].device
+        self._offsets = offsets
+        # Backward in three pieces when several ranks run (see _phases): [0, i_bb) everything but the backbone,
+        # [i_l4, end) layer4, [i_bb, i_l4) layer2-3 -- each a contiguous slice of the flat gradient
+        i_bb = next((i for i, p in enumerate(self.params) if is_bb(p)), len(self.params))
+        i_l4 = next((i for i, p in enumerate(self.params) if is_bb(p) and ".layer4." in names[id(p)]), len(self.params))
+        trunk = getattr(getattr(model, "backbone", [None])[0], "body", None)
+        contiguous_tail = all(is_bb(p) for p in self.params[i_bb:]) and \
+            all(".layer4." in names[id(p)] for p in self.params[i_l4:])
+        self.phased = (self.world > 1 and os.environ.get("TFB200_OVERLAP_AR", "1") != "0" and trunk is not None
+                       and hasattr(trunk, "cut") and 0 < i_bb < i_l4 < len(self.params) and contiguous_tail)
+        self._trunk, self._i_bb, self._i_l4 = trunk, i_bb, i_l4
+        off_bb = offsets[i_bb] if i_bb < len(offsets) else total
+        off_l4 = offsets[i_l4] if i_l4 < len(offsets) else total
+        self._ranges3 = ((0, off_bb), (off_l4, total), (off_bb, off_l4))
+        self._comm_stream = None
 
         def flat_view(buf, p, o):
             chunk = buf[o:o + p.numel()]
@@ -108,6 +130,7 @@ class TrainStep:
         self.flat_grad = torch.zeros(total, dtype=torch.float32, device=dev)
         for p, o in zip(self.params, offsets):
             p.grad = flat_view(self.flat_grad, p, o)
+        self._views = [p.grad for p in self.params]
         self.flat_param = None
         self.flat_optimizer = None
         if groups is not None:
@@ -168,18 +191,122 @@ class TrainStep:
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):                                            # memos, lazy inits
             for _ in range(2):
-                lg, bx = self.core(self.static_frames)
-                self._loss(lg, bx, self.s_targets, self.s_num_boxes).backward()
+                if self.phased:
+                    self._phase_a(self.static_frames, self.s_targets, self.s_num_boxes)
+                    self._phase_b()
+                    self._phase_c()
+                else:
+                    lg, bx = self.core(self.static_frames)
+                    self._loss(lg, bx, self.s_targets, self.s_num_boxes).backward()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g, pool=self._pool):
-            lg, bx = self.core(self.static_frames)
-            loss = self._loss(lg, bx, self.s_targets, self.s_num_boxes)
-            self._backward_into_flat(loss)
-            self.s_loss = loss.detach()
+        if self.phased:
+            # three graphs: the gradient slice each one finishes is all-reduced while the next one replays
+            with torch.cuda.graph(g, pool=self._pool):
+                self.s_loss = self._phase_a(self.static_frames, self.s_targets, self.s_num_boxes)
+            self.g_pb, self.g_pc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.g_pb, pool=self._pool):
+                self._phase_b()
+            with torch.cuda.graph(self.g_pc, pool=self._pool):
+                self._phase_c()
+        else:
+            with torch.cuda.graph(g, pool=self._pool):
+                lg, bx = self.core(self.static_frames)
+                loss = self._loss(lg, bx, self.s_targets, self.s_num_boxes)
+                self._backward_into_flat(loss)
+                self.s_loss = loss.detach()
         self.g_full = g
         self.flat_grad.zero_()
+
+    # ------------------------------------------------------------------------------------------ phased backward
+    # With several ranks the backward runs in three pieces so that the NCCL all-reduce of a finished slice of the flat
+    # gradient overlaps the rest of the backward (what DistributedDataParallel's buckets give the reference,
+    # src/train.py:86-89):   A  forward + loss + backward of everything but the backbone   -> slice [transformer]
+    #                        B  backward of layer4                                           -> slice [layer4]
+    #                        C  backward of layer3 + layer2                                  -> slice [layer2-3]
+    # The trunk hands the transformer (and layer4) DETACHED copies of its stage outputs (backbone.py `cut`), so each
+    # piece is an ordinary autograd.grad call whose cotangents come from the previous piece.  Same values as the
+    # monolithic backward (the chain rule, evaluated in the same order).
+    def _gather(self, first: int, params, grads) -> None:
+        views = self._views[first:first + len(params)]
+        dst = [v for v, g in zip(views, grads) if g is not None]
+        src = [g for g in grads if g is not None]
+        if dst:
+            torch._foreach_copy_(dst, src)
+        for v, g in zip(views, grads):
+            if g is None:
+                v.zero_()
+
+    def _phase_a(self, frames, targets, num_boxes):
+        rec = {}
+
+        def cut(tag, t):
+            if not t.requires_grad:
+                return t
+            leaf = t.detach().requires_grad_(True)
+            rec[tag] = (t, leaf)
+            return leaf
+        self._trunk.cut = cut
+        try:
+            logits, boxes = self.core(frames)
+        finally:
+            self._trunk.cut = None
+        loss = self._loss(logits, boxes, targets, num_boxes)
+        head = self.params[:self._i_bb]
+        tags = list(rec)
+        grads = torch.autograd.grad(loss, head + [rec[t][1] for t in tags], allow_unused=True)
+        self._gather(0, head, grads[:len(head)])
+        self._cut_out = {t: rec[t][0] for t in tags}
+        self._cut_leaf = {t: rec[t][1] for t in tags}
+        self._cut_grad = dict(zip(tags, grads[len(head):]))
+        return loss.detach()
+
+    def _phase_b(self) -> None:
+        tail = self.params[self._i_l4:]
+        x4, g4 = self._cut_out.get("layer4/tap"), self._cut_grad.get("layer4/tap")
+        nxt = self._cut_leaf.get("layer3/next")
+        self._g_next = None
+        if x4 is None or g4 is None:
+            self._gather(self._i_l4, tail, [None] * len(tail))
+            return
+        grads = torch.autograd.grad([x4], tail + ([nxt] if nxt is not None else []), grad_outputs=[g4], allow_unused=True)
+        self._gather(self._i_l4, tail, grads[:len(tail)])
+        if nxt is not None:
+            self._g_next = grads[len(tail)]
+
+    def _phase_c(self) -> None:
+        mid = self.params[self._i_bb:self._i_l4]
+        outs, cots = [], []
+        x3 = self._cut_out.get("layer3/tap", self._cut_out.get("layer3/next"))
+        g3 = self._cut_grad.get("layer3/tap")
+        if self._g_next is not None:
+            g3 = self._g_next if g3 is None else g3 + self._g_next
+        if x3 is not None and g3 is not None:
+            outs.append(x3)
+            cots.append(g3)
+        x2, g2 = self._cut_out.get("layer2/tap"), self._cut_grad.get("layer2/tap")
+        if x2 is not None and g2 is not None:
+            outs.append(x2)
+            cots.append(g2)
+        if not outs:
+            self._gather(self._i_bb, mid, [None] * len(mid))
+            return
+        self._gather(self._i_bb, mid, torch.autograd.grad(outs, mid, grad_outputs=cots, allow_unused=True))
+
+    def _all_reduce_slice(self, which: int):
+        """start the all-reduce of one of the three gradient slices on the communication stream"""
+        a, b = self._ranges3[which]
+        if b <= a:
+            return None
+        view = self.flat_grad[a:b]
+        if view.is_cuda:
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream()
+            self._comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._comm_stream):
+                return dist.all_reduce(view, async_op=True)
+        return dist.all_reduce(view, async_op=True)
 
     def _backward_into_flat(self, loss: torch.Tensor) -> None:
         """``loss.backward()`` leaving the gradient in ``flat_grad``.
@@ -226,6 +353,7 @@ class TrainStep:
         full = self.g_full is not None and tuple(len(t["labels"]) for t in targets) == self.full_sizes
         # one scalar all-reduce per step on EVERY path, before anything else (same collective order on all ranks)
         num_boxes = self._normaliser(targets, dev) if (self.world > 1 or full) else None
+        pending = None
         if full:
             if frames is not self.static_frames:
                 self.static_frames.copy_(frames, non_blocking=True)     # device or pinned-host source
@@ -235,6 +363,19 @@ class TrainStep:
                     st["labels"].copy_(t["labels"], non_blocking=True)
             self.g_full.replay()
             loss = self.s_loss
+            if self.phased:
+                pending = [self._all_reduce_slice(0)]
+                self.g_pb.replay()
+                pending.append(self._all_reduce_slice(1))
+                self.g_pc.replay()
+                pending.append(self._all_reduce_slice(2))
+        elif self.phased and self.g_fwd is None:
+            loss = self._phase_a(frames, targets, num_boxes)
+            pending = [self._all_reduce_slice(0)]
+            self._phase_b()
+            pending.append(self._all_reduce_slice(1))
+            self._phase_c()
+            pending.append(self._all_reduce_slice(2))
         elif self.g_fwd is not None:
             if frames is not self.static_frames:
                 self.static_frames.copy_(frames, non_blocking=True)     # device or pinned-host source
@@ -251,7 +392,15 @@ class TrainStep:
             loss = self._loss(logits, boxes, targets, num_boxes)
             self._backward_into_flat(loss)
         if self.world > 1:
-            dist.all_reduce(self.flat_grad)
+            if self.phased:
+                # every path issues the SAME three collectives in the same order (ranks may take different paths)
+                if pending is None:
+                    pending = [self._all_reduce_slice(i) for i in range(3)]
+                for work in pending:
+                    if work is not None:
+                        work.wait()
+            else:
+                dist.all_reduce(self.flat_grad)
             self.flat_grad.div_(self.world)
         if self.optimizer is not None:
             if self.max_norm > 0:
