@@ -133,6 +133,26 @@ int tfb200_refine_boxes_fwd_f32(const float* delta, const float* ref, float* out
 int tfb200_refine_boxes_bwd_f32(const float* grad_out, const float* out, const float* ref, float* grad_delta,
                                 float* grad_ref, int64_t rows, int ref_dim, float eps, void* stream);
 
+/* SetCriterion / HungarianMatcher on the device (csrc/set_loss.cu; reference: models/matcher.py:60-100,
+ * models/detr.py:213-328, util/misc.py:540-571, util/box_ops.py:24-61).  R = K*B*Q rows (layer, image, query).
+ *   match_cost : cost[R][T] = w_bbox * L1 + w_class * focal class cost - w_giou * GIoU against the T boxes of the batch
+ *   set_loss_fwd: src/tgt [K][T] are the matched (query, global box) pairs, columns offsets[b]..offsets[b+1]-1 belong to
+ *                 image b; writes out5k[5][K] = loss_ce, loss_bbox, loss_giou, cardinality_error, class_error and the
+ *                 UNIT gradients (unit_logits [R][C], unit_l1 / unit_giou [R][4]) that set_loss_bwd scales by the incoming
+ *                 gradients g_*[K] / num_boxes.  n_gt [B] = boxes per image (float), num_boxes = device scalar.
+ *                 row_loss [R], row_flags [R], pair_l1 / pair_giou [K][T] are scratch.                                  */
+int tfb200_match_cost_f32(const float* logits, const float* boxes, const int64_t* tgt_ids, const float* tgt_boxes,
+                          float* cost, int64_t R, int C, int T, float w_class, float w_bbox, float w_giou, float alpha,
+                          float gamma, void* stream);
+int tfb200_set_loss_fwd_f32(const float* logits, const float* boxes, const int64_t* src, const int64_t* tgt,
+                            const int64_t* tgt_ids, const float* tgt_boxes, const int* offsets, const float* n_gt,
+                            const float* num_boxes, float* unit_logits, float* unit_l1, float* unit_giou, float* row_loss,
+                            int* row_flags, float* pair_l1, float* pair_giou, float* out5k, int K, int B, int Q, int C,
+                            int T, float alpha, float gamma, void* stream);
+int tfb200_set_loss_bwd_f32(const float* unit_logits, const float* unit_l1, const float* unit_giou, const float* g_ce,
+                            const float* g_l1, const float* g_giou, const float* num_boxes, float* grad_logits,
+                            float* grad_boxes, int K, int B, int Q, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,31 @@ from .util import (accuracy, box_cxcywh_to_xyxy, generalized_box_iou, get_world_
                    is_dist_avail_and_initialized, paired_giou, sigmoid_focal_loss)
 
 
+
+# SetCriterion losses (+ their backward) as fused device kernels (csrc/set_loss.cu); off until validated on a B200
+_FUSED_LOSS = os.environ.get("TFB200_FUSED_LOSS", "0") != "0"
+
+
+class _SetLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, boxes, src, tgt, tgt_ids, tgt_boxes, offsets, n_gt, num_boxes, alpha, gamma):
+        from . import ext
+        out, ul, u1, ug = ext.load().set_loss_forward(logits, boxes, src, tgt, tgt_ids, tgt_boxes, offsets, n_gt,
+                                                      num_boxes, alpha, gamma)
+        ctx.save_for_backward(ul, u1, ug, num_boxes)
+        ce, l1, giou, card, cerr = out.unbind(0)
+        ctx.mark_non_differentiable(card, cerr)
+        return ce, l1, giou, card, cerr
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_ce, g_l1, g_giou, _g_card, _g_err):
+        from . import ext
+        ul, u1, ug, num_boxes = ctx.saved_tensors
+        gl, gb = ext.load().set_loss_backward(ul, u1, ug, g_ce.contiguous(), g_l1.contiguous(), g_giou.contiguous(),
+                                              num_boxes)
+        return gl, gb, None, None, None, None, None, None, None, None, None
+
 class SetCriterion(nn.Module):
     def __init__(self, num_classes, matcher, weight_dict, eos_coef, losses, focal_loss, focal_alpha,
                  focal_gamma, tracking, track_query_false_positive_eos_weight):
@@ -158,6 +183,33 @@ class SetCriterion(nn.Module):
             return out
         return t
 
+    def _fused_losses(self, logits, boxes, src2d, tgt2d, targets, sizes, n_gt, num_boxes):
+        """The loss values of ``forward_stacked`` and their gradients from three launches (csrc/set_loss.cu)."""
+        k = logits.shape[0]
+        dev = logits.device
+        key = ("off", tuple(sizes), dev)
+        off = self._index_memo.get(key)
+        if off is None:
+            acc = [0]
+            for n in sizes:
+                acc.append(acc[-1] + n)
+            off = self._index_memo[key] = torch.tensor(acc, dtype=torch.int32, device=dev)
+        if not torch.is_tensor(num_boxes):
+            num_boxes = torch.tensor(float(num_boxes), dtype=torch.float32, device=dev)
+        tgt_ids = torch.cat([t["labels"] for t in targets])
+        tgt_boxes = torch.cat([t["boxes"] for t in targets]).float()
+        ce, l1, gi, card, cerr = _SetLoss.apply(logits, boxes, src2d, tgt2d, tgt_ids, tgt_boxes, off, n_gt,
+                                                num_boxes.reshape(1).float(), float(self.focal_alpha),
+                                                float(self.focal_gamma))
+        losses = {"loss_ce": ce[-1], "class_error": cerr[-1], "loss_bbox": l1[-1], "loss_giou": gi[-1],
+                  "cardinality_error": card[-1]}
+        for i in range(k - 1):
+            losses[f"loss_ce_{i}"] = ce[i]
+            losses[f"loss_bbox_{i}"] = l1[i]
+            losses[f"loss_giou_{i}"] = gi[i]
+            losses[f"cardinality_error_{i}"] = card[i]
+        return losses
+
     def forward_stacked(self, logits, boxes, targets, num_boxes=None):
         """Same losses as ``forward`` for a detector whose K decoder layers arrive stacked --
         ``logits [K,B,Q,C]``, ``boxes [K,B,Q,4]``, last layer = final prediction -- computed in ONE pass over
@@ -206,6 +258,8 @@ class SetCriterion(nn.Module):
             idx = torch.stack([lay, bat, src, tgt]).to(dev, non_blocking=True)
             lay, bat, src, tgt = idx[0], idx[1], idx[2], idx[3]
             n_gt = torch.as_tensor(sizes, device=dev, dtype=torch.float)
+        if device_match is not None and _FUSED_LOSS and logits.dtype == torch.float32:
+            return self._fused_losses(logits, boxes, src2d, tgt2d, targets, sizes, n_gt, num_boxes)
         gt_labels = torch.cat([t["labels"] for t in targets])[tgt]
         gt_boxes = torch.cat([t["boxes"] for t in targets])[tgt]
 

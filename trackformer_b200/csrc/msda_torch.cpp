@@ -383,6 +383,70 @@ std::vector<at::Tensor> lsa(const at::Tensor& cost, const at::Tensor& offsets, i
   return {src, tgt, status};
 }
 
+// ---- SetCriterion / matcher on the device (csrc/set_loss.cu) ------------------------------------------------------------
+at::Tensor match_cost(const at::Tensor& logits, const at::Tensor& boxes, const at::Tensor& tgt_ids, const at::Tensor& tgt_boxes,
+                      double w_class, double w_bbox, double w_giou, double alpha, double gamma) {
+  TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == at::kFloat && boxes.scalar_type() == at::kFloat &&
+              tgt_ids.scalar_type() == at::kLong && tgt_boxes.scalar_type() == at::kFloat, "match_cost: dtypes");
+  const at::Tensor lg = logits.contiguous(), bx = boxes.contiguous(), ti = tgt_ids.contiguous(), tb = tgt_boxes.contiguous();
+  const int64_t C = lg.size(-1), R = lg.numel() / C, T = ti.numel();
+  TORCH_CHECK(bx.numel() == R * 4 && tb.numel() == T * 4 && T > 0, "match_cost: shapes");
+  const c10::cuda::CUDAGuard guard(logits.device());
+  at::Tensor cost = at::empty({R, T}, lg.options());
+  const int rc = tfb200_match_cost_f32(lg.data_ptr<float>(), bx.data_ptr<float>(), ti.data_ptr<int64_t>(), tb.data_ptr<float>(),
+                                       cost.data_ptr<float>(), R, int(C), int(T), float(w_class), float(w_bbox), float(w_giou),
+                                       float(alpha), float(gamma), c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "match_cost failed (code ", rc, ")");
+  return cost;
+}
+
+// returns {out5k [5][K], unit_logits [K,B,Q,C], unit_l1 [K,B,Q,4], unit_giou [K,B,Q,4]}
+std::vector<at::Tensor> set_loss_forward(const at::Tensor& logits, const at::Tensor& boxes, const at::Tensor& src,
+                                         const at::Tensor& tgt, const at::Tensor& tgt_ids, const at::Tensor& tgt_boxes,
+                                         const at::Tensor& offsets, const at::Tensor& n_gt, const at::Tensor& num_boxes,
+                                         double alpha, double gamma) {
+  TORCH_CHECK(logits.is_cuda() && logits.dim() == 4 && boxes.dim() == 4 && logits.scalar_type() == at::kFloat &&
+              boxes.scalar_type() == at::kFloat && src.scalar_type() == at::kLong && tgt.scalar_type() == at::kLong &&
+              tgt_ids.scalar_type() == at::kLong && tgt_boxes.scalar_type() == at::kFloat &&
+              offsets.scalar_type() == at::kInt && n_gt.scalar_type() == at::kFloat && num_boxes.scalar_type() == at::kFloat &&
+              num_boxes.is_cuda() && n_gt.is_cuda() && offsets.is_cuda(), "set_loss_forward: dtypes / devices");
+  const at::Tensor lg = logits.contiguous(), bx = boxes.contiguous(), s = src.contiguous(), t = tgt.contiguous();
+  const at::Tensor ti = tgt_ids.contiguous(), tb = tgt_boxes.contiguous();
+  const int64_t K = lg.size(0), B = lg.size(1), Q = lg.size(2), C = lg.size(3), T = s.size(-1);
+  TORCH_CHECK(s.numel() == K * T && t.numel() == K * T && ti.numel() == T && tb.numel() == 4 * T && offsets.numel() == B + 1 &&
+              n_gt.numel() == B, "set_loss_forward: shapes");
+  const c10::cuda::CUDAGuard guard(logits.device());
+  at::Tensor out = at::empty({5, K}, lg.options());
+  at::Tensor ul = at::empty_like(lg), u1 = at::empty_like(bx), ug = at::empty_like(bx);
+  at::Tensor row_loss = at::empty({K * B * Q}, lg.options()), row_flags = at::empty({K * B * Q}, lg.options().dtype(at::kInt));
+  at::Tensor pl = at::zeros({K, T}, lg.options()), pg = at::zeros({K, T}, lg.options());
+  const int rc = tfb200_set_loss_fwd_f32(lg.data_ptr<float>(), bx.data_ptr<float>(), s.data_ptr<int64_t>(), t.data_ptr<int64_t>(),
+                                         ti.data_ptr<int64_t>(), tb.data_ptr<float>(), offsets.data_ptr<int>(),
+                                         n_gt.data_ptr<float>(), num_boxes.data_ptr<float>(), ul.data_ptr<float>(),
+                                         u1.data_ptr<float>(), ug.data_ptr<float>(), row_loss.data_ptr<float>(),
+                                         row_flags.data_ptr<int>(), pl.data_ptr<float>(), pg.data_ptr<float>(),
+                                         out.data_ptr<float>(), int(K), int(B), int(Q), int(C), int(T), float(alpha),
+                                         float(gamma), c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "set_loss_forward failed (code ", rc, ")");
+  return {out, ul, u1, ug};
+}
+
+std::vector<at::Tensor> set_loss_backward(const at::Tensor& unit_logits, const at::Tensor& unit_l1, const at::Tensor& unit_giou,
+                                          const at::Tensor& g_ce, const at::Tensor& g_l1, const at::Tensor& g_giou,
+                                          const at::Tensor& num_boxes) {
+  const int64_t K = unit_logits.size(0), B = unit_logits.size(1), Q = unit_logits.size(2), C = unit_logits.size(3);
+  const at::Tensor a = g_ce.contiguous(), b = g_l1.contiguous(), c = g_giou.contiguous();
+  TORCH_CHECK(a.numel() == K && b.numel() == K && c.numel() == K && a.scalar_type() == at::kFloat, "set_loss_backward: gradient vectors [K]");
+  const c10::cuda::CUDAGuard guard(unit_logits.device());
+  at::Tensor gl = at::empty_like(unit_logits), gb = at::empty_like(unit_l1);
+  const int rc = tfb200_set_loss_bwd_f32(unit_logits.data_ptr<float>(), unit_l1.data_ptr<float>(), unit_giou.data_ptr<float>(),
+                                         a.data_ptr<float>(), b.data_ptr<float>(), c.data_ptr<float>(),
+                                         num_boxes.data_ptr<float>(), gl.data_ptr<float>(), gb.data_ptr<float>(), int(K), int(B),
+                                         int(Q), int(C), c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "set_loss_backward failed (code ", rc, ")");
+  return {gl, gb};
+}
+
 // ---- detection post-processing for the tracker (deformable_detr.py:286-334) ------------------------------------------
 std::vector<at::Tensor> detect_postprocess(const at::Tensor& logits, const at::Tensor& boxes, const at::Tensor& sizes_hw) {
   TORCH_CHECK(logits.is_cuda() && logits.scalar_type() == at::kFloat && logits.dim() == 3, "detect_postprocess: logits must be [N,Q,C] fp32 CUDA");
@@ -525,6 +589,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("add_dropout_layernorm_seeded_backward", &add_dropout_layernorm_seeded_backward);
   m.def("colsum", &colsum);
   m.def("lsa", &lsa);
+  m.def("match_cost", &match_cost);
+  m.def("set_loss_forward", &set_loss_forward);
+  m.def("set_loss_backward", &set_loss_backward);
   m.def("sampling_prep_forward", &sampling_prep_forward);
   m.def("sampling_prep_backward", &sampling_prep_backward);
   m.def("refine_boxes_forward", &refine_boxes_forward);

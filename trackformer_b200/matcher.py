@@ -8,12 +8,17 @@ query is pinned to the ground-truth box of its identity.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 from scipy.optimize import linear_sum_assignment
 from torch import nn
 
 from .util import box_cxcywh_to_xyxy, generalized_box_iou
+
+# matching cost and SetCriterion losses as fused device kernels (csrc/set_loss.cu); off until validated on a B200
+_FUSED_LOSS = os.environ.get("TFB200_FUSED_LOSS", "0") != "0"
 
 
 class HungarianMatcher(nn.Module):
@@ -79,7 +84,12 @@ class HungarianMatcher(nn.Module):
             return None
         tgt_ids = torch.cat([t["labels"] for t in targets])
         tgt_boxes = torch.cat([t["boxes"] for t in targets])
-        cost = self._cost(logits.flatten(0, 2), boxes.flatten(0, 2), tgt_ids, tgt_boxes).view(k, bs, nq, -1)
+        if _FUSED_LOSS and self.focal_loss and logits.dtype == torch.float32:
+            # the whole cost matrix in one launch (csrc/set_loss.cu) instead of ~25 elementwise kernels
+            cost = ext.load().match_cost(logits, boxes, tgt_ids, tgt_boxes.float(), self.cost_class, self.cost_bbox,
+                                         self.cost_giou, self.focal_alpha, self.focal_gamma).view(k, bs, nq, -1)
+        else:
+            cost = self._cost(logits.flatten(0, 2), boxes.flatten(0, 2), tgt_ids, tgt_boxes).view(k, bs, nq, -1)
         key = (tuple(sizes), logits.device)
         off = self._offsets_memo.get(key)
         if off is None:
