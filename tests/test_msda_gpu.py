@@ -405,13 +405,13 @@ def test_tiled_encoder_forward_equals_general_kernel(msda, dev, name):
 
 
 # ----------------------------------------------------------------------------- every fp32 / D = 32 kernel family
-def _encoder_problem(name):
+def _encoder_problem(name, D=32):
     N, M, hw, P, dist = TILE_CASES[name]
     g = torch.Generator().manual_seed(100 + len(name))
     shapes = torch.as_tensor(hw, dtype=torch.long)
     L = len(hw)
     S = int((shapes[:, 0] * shapes[:, 1]).sum())
-    value = torch.randn(N, S, M, 32, generator=g)
+    value = torch.randn(N, S, M, D, generator=g)
     if dist == "uniform":
         loc = torch.rand(N, S, M, L, P, 2, generator=g) * 1.2 - 0.1
     else:
@@ -427,7 +427,7 @@ def _encoder_problem(name):
         loc = ref + off / shapes.flip(-1).float()[None, None, None, :, None, :]
     attn = torch.softmax(torch.randn(N, S, M, L * P, generator=g), -1).view(N, S, M, L, P)
     attn[:, ::7, 1] = 0.0                                     # exact-zero attention rows (skipped reductions)
-    gout = torch.randn(N, S, M * 32, generator=g)
+    gout = torch.randn(N, S, M * D, generator=g)
     return value, shapes, loc, attn, gout
 
 
@@ -497,3 +497,28 @@ def test_d32_kernels_with_64_samples_per_query(msda, dev):
         msda.set_variant(0, 0)
     np.testing.assert_allclose(ga.cpu().numpy(), ref_ga, **F32)
     np.testing.assert_allclose(gv.cpu().numpy(), ref_gv, rtol=F32["rtol"], atol=F32["atol"] * max(1.0, float(np.abs(ref_gv).max())))
+
+
+@pytest.mark.parametrize("variant", [0, 100, 101])
+@pytest.mark.parametrize("name", ["c1_enc", "odd_sizes", "wide_offsets", "heads4", "l8_p4"])
+def test_run_kernels_d36_match_c_oracle(msda, dev, name, variant):
+    """the published TrackFormer geometry (hidden 288, D = 36: nine lanes per head row, three runs per warp), forward
+    and fused backward of the run kernels against the C oracle"""
+    from oracle import msda_oracle
+    value, shapes, loc, attn, gout = _encoder_problem(name, D=36)
+    ref_out = msda_oracle.msda_forward(value.numpy(), shapes.numpy(), loc.numpy(), attn.numpy())
+    ref_gv, ref_gl, ref_ga = msda_oracle.msda_backward(value.numpy(), shapes.numpy(), loc.numpy(), attn.numpy(),
+                                                       gout.numpy())
+    tv, ts, tl, ta, tg = (x.to(dev) for x in (value, shapes, loc, attn, gout))
+    msda.set_variant(variant, variant)
+    try:
+        out = msda.ms_deform_attn_forward(tv, ts, tl, ta, 64)
+        gv, gl, ga = msda.ms_deform_attn_backward(tv, ts, tl, ta, tg, 64)
+        torch.cuda.synchronize()
+    finally:
+        msda.set_variant(0, 0)
+    np.testing.assert_allclose(out.cpu().numpy(), ref_out, **F32)
+    scale = max(1.0, float(np.abs(ref_gv).max()))
+    np.testing.assert_allclose(gv.cpu().numpy(), ref_gv, rtol=F32["rtol"], atol=F32["atol"] * scale)
+    np.testing.assert_allclose(ga.cpu().numpy(), ref_ga, **F32)
+    np.testing.assert_allclose(gl.cpu().numpy(), ref_gl, rtol=F32["rtol"] * 5, atol=F32["atol"] * 50)

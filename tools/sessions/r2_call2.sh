@@ -10,8 +10,8 @@ timeout 900 python tools/opbench.py --cases c2_enc_init,c2_enc_smooth,c2_enc_mod
    --variants 0,100,101,110,20 --bwd-variants 0,100,101,110,20 --iters 20 --out gpurun_out/r2_opbench_v1.json 2>&1 | cut -c1-230
 echo "=== tcgen05 GEMM (own timeout: a wrong barrier would hang)"
 timeout 300 python tools/gemm_bench.py --iters 10 2>&1 | cut -c1-400 | tail -12
-echo "=== prep tests"
-timeout 900 python -m pytest tests/test_fused_bn_gpu.py tests/test_fused_norm_gpu.py tests/test_train_step_gpu.py -q 2>&1 | tail -5
+echo "=== prep tests + fused loss / refine tests"
+timeout 900 python -m pytest tests/test_fused_loss_gpu.py tests/test_fused_bn_gpu.py tests/test_fused_norm_gpu.py tests/test_train_step_gpu.py -q 2>&1 | tail -8
 run() {
   local name=$1; shift
   env "$@" timeout 600 python bench.py --steps 40 --warmup 5 --no-cpu-baseline 2>gpurun_out/bench_r2_${name}.err | tee gpurun_out/bench_r2_${name}.json | cut -c1-170
@@ -20,6 +20,10 @@ run all_on      TFB200_FUSED_BN=1 TFB200_GATHER_GRADS=1 TFB200_LN_SEEDED=1
 run no_fused_bn TFB200_FUSED_BN=0 TFB200_GATHER_GRADS=1 TFB200_LN_SEEDED=1
 run no_gather   TFB200_FUSED_BN=1 TFB200_GATHER_GRADS=0 TFB200_LN_SEEDED=1
 run no_seeded   TFB200_FUSED_BN=1 TFB200_GATHER_GRADS=1 TFB200_LN_SEEDED=0
+run fused_loss  TFB200_FUSED_LOSS=1
+run tcgen05     TFB200_TCGEN05_LINEAR=1
+run tcgen05_f   TFB200_TCGEN05_LINEAR=1 TFB200_TCGEN05_PARTS=f
+run both        TFB200_FUSED_LOSS=1 TFB200_TCGEN05_LINEAR=1
 echo "=== model parity (incl. the new full-size cases)"
 timeout 1500 python -m pytest tests/test_model_parity_gpu.py tests/test_tracker_gpu.py -q -s 2>&1 | grep -v "^$" | tail -40
 echo "=== ncu launch list of the step graph (kernel nodes)"

@@ -295,33 +295,50 @@ static int forward_impl(const T* value, const int64_t* shapes, const T* loc, con
   auto grid_for = [&](int G) { return unsigned((groups * G + kThreads - 1) / kThreads); };
   bool launched = false;
   if constexpr (sizeof(T) == 4) {
+    // run kernels (msda_run.cuh): large query sets, D = 32 (8 lanes per head row) or D = 36 (9 lanes)
+    const int variant = g_fwd_variant.load(std::memory_order_relaxed);
+    const int LP = d.L * d.P;
+    if (variant != 1 && vec_ok && (d.D == 32 || d.D == 36) && LP <= kMaxLP && aligned16(loc) && aligned16(attn) &&
+        groups < (int64_t(1) << 31)) {
+      const Family fam = pick_family(variant, groups, d);
+      if (fam == Family::kRun8 || fam == Family::kRun4) {
+        const int R = fam == Family::kRun8 ? 8 : 4, LG = d.D / 4;
+        const int QB = run_runs(LG) * R;
+        const int qblocks = (d.Lq + QB - 1) / QB;
+        const int64_t units = int64_t(d.N) * qblocks * (d.M / kRunHeads);
+        const size_t smem = fwd_run_smem_bytes(LG, R, LP);
+        if (units < (int64_t(1) << 31) && smem <= 220 * 1024) {
+#define MSDA_FWD_RUN(LG_, R_, LPCT_)                                                                                \
+  do {                                                                                                              \
+    MSDA_ENSURE_SMEM((msda_fwd_run_kernel<LG_, R_, LPCT_>), smem);                                                  \
+    msda_fwd_run_kernel<LG_, R_, LPCT_><<<unsigned(units), kRunThreads, smem, st>>>(value, shapes, loc, attn, out,   \
+                                                                                   d.S, d.M, d.L, d.Lq, d.P, qblocks); \
+  } while (0)
+          if (LG == 8) {
+            if (R == 8 && LP == 16) MSDA_FWD_RUN(8, 8, 16);
+            else if (R == 8) MSDA_FWD_RUN(8, 8, 0);
+            else if (LP == 16) MSDA_FWD_RUN(8, 4, 16);
+            else MSDA_FWD_RUN(8, 4, 0);
+          } else {
+            if (R == 8 && LP == 16) MSDA_FWD_RUN(9, 8, 16);
+            else if (R == 8) MSDA_FWD_RUN(9, 8, 0);
+            else if (LP == 16) MSDA_FWD_RUN(9, 4, 16);
+            else MSDA_FWD_RUN(9, 4, 0);
+          }
+#undef MSDA_FWD_RUN
+          g_launches.fetch_add(1, std::memory_order_relaxed);
+          return int(cudaGetLastError());
+        }
+      }
+    }
+  }
+  if constexpr (sizeof(T) == 4) {
     // specialised kernels for the shipped geometry (fp32, 128-byte head rows); variant 1 forces the generic path
     const int variant = g_fwd_variant.load(std::memory_order_relaxed);
     const int LP = d.L * d.P;
     if (variant != 1 && vec_ok && d.D == 32 && LP <= kMaxLP && aligned16(loc) && aligned16(attn) &&
         groups < (int64_t(1) << 31)) {
       const Family fam = pick_family(variant, groups, d);
-      if (fam == Family::kRun8 || fam == Family::kRun4) {
-        const int R = fam == Family::kRun8 ? 8 : 4;
-        const int qblocks = (d.Lq + 4 * R - 1) / (4 * R);
-        const int64_t units = int64_t(d.N) * qblocks * (d.M / kRunHeads);
-        if (units < (int64_t(1) << 31)) {
-          const size_t smem = fwd_run_smem_bytes(R, LP);
-#define MSDA_FWD_RUN(R_, LPCT_)                                                                                     \
-  do {                                                                                                              \
-    MSDA_ENSURE_SMEM((msda_fwd_run_kernel<R_, LPCT_>), smem);                                                       \
-    msda_fwd_run_kernel<R_, LPCT_><<<unsigned(units), kRunThreads, smem, st>>>(value, shapes, loc, attn, out, d.S,   \
-                                                                              d.M, d.L, d.Lq, d.P, qblocks);        \
-  } while (0)
-          if (R == 8 && LP == 16) MSDA_FWD_RUN(8, 16);
-          else if (R == 8) MSDA_FWD_RUN(8, 0);
-          else if (LP == 16) MSDA_FWD_RUN(4, 16);
-          else MSDA_FWD_RUN(4, 0);
-#undef MSDA_FWD_RUN
-          g_launches.fetch_add(1, std::memory_order_relaxed);
-          return int(cudaGetLastError());
-        }
-      }
       if (fam == Family::kWide) {
         const unsigned grid = unsigned((groups + kWideThreads / 32 - 1) / (kWideThreads / 32));
         msda_fwd_wide_kernel<<<grid, kWideThreads, 0, st>>>(value, shapes, loc, attn, out, d.S, d.M, d.L, d.Lq, d.P,
@@ -420,30 +437,46 @@ static int backward_impl(const T* value, const int64_t* shapes, const T* loc, co
   if constexpr (sizeof(T) == 4) {
     const int variant = g_bwd_variant.load(std::memory_order_relaxed);
     const int LP = d.L * d.P;
-    if (variant != 1 && vec_ok && d.D == 32 && LP <= kMaxLP && aligned16(loc) && aligned16(attn) &&
+    if (variant != 1 && vec_ok && (d.D == 32 || d.D == 36) && LP <= kMaxLP && aligned16(loc) && aligned16(attn) &&
         aligned16(gloc) && aligned16(gattn) && groups < (int64_t(1) << 31)) {
       const Family fam = pick_family(variant, groups, d);
       if (fam == Family::kRun8 || fam == Family::kRun4) {
-        const int R = fam == Family::kRun8 ? 8 : 4;
-        const int qblocks = (d.Lq + 4 * R - 1) / (4 * R);
+        const int R = fam == Family::kRun8 ? 8 : 4, LG = d.D / 4;
+        const int QB = run_runs(LG) * R;
+        const int qblocks = (d.Lq + QB - 1) / QB;
         const int64_t units = int64_t(d.N) * qblocks * (d.M / kRunHeads);
-        if (units < (int64_t(1) << 31)) {
-          const size_t smem = bwd_run_smem_bytes(R, LP);
-#define MSDA_BWD_RUN(R_, LPCT_)                                                                                     \
+        const size_t smem = bwd_run_smem_bytes(LG, R, LP);
+        if (units < (int64_t(1) << 31) && smem <= 220 * 1024) {
+#define MSDA_BWD_RUN(LG_, R_, LPCT_)                                                                                \
   do {                                                                                                              \
-    MSDA_ENSURE_SMEM((msda_bwd_run_kernel<R_, LPCT_>), smem);                                                       \
-    msda_bwd_run_kernel<R_, LPCT_><<<unsigned(units), kRunThreads, smem, st>>>(                                     \
+    MSDA_ENSURE_SMEM((msda_bwd_run_kernel<LG_, R_, LPCT_>), smem);                                                  \
+    msda_bwd_run_kernel<LG_, R_, LPCT_><<<unsigned(units), kRunThreads, smem, st>>>(                                \
         value, shapes, loc, attn, gout, gval, gloc, gattn, d.S, d.M, d.L, d.Lq, d.P, qblocks);                      \
   } while (0)
-          if (R == 8 && LP == 16) MSDA_BWD_RUN(8, 16);
-          else if (R == 8) MSDA_BWD_RUN(8, 0);
-          else if (LP == 16) MSDA_BWD_RUN(4, 16);
-          else MSDA_BWD_RUN(4, 0);
+          if (LG == 8) {
+            if (R == 8 && LP == 16) MSDA_BWD_RUN(8, 8, 16);
+            else if (R == 8) MSDA_BWD_RUN(8, 8, 0);
+            else if (LP == 16) MSDA_BWD_RUN(8, 4, 16);
+            else MSDA_BWD_RUN(8, 4, 0);
+          } else {
+            if (R == 8 && LP == 16) MSDA_BWD_RUN(9, 8, 16);
+            else if (R == 8) MSDA_BWD_RUN(9, 8, 0);
+            else if (LP == 16) MSDA_BWD_RUN(9, 4, 16);
+            else MSDA_BWD_RUN(9, 4, 0);
+          }
 #undef MSDA_BWD_RUN
           g_launches.fetch_add(1, std::memory_order_relaxed);
           return int(cudaGetLastError());
         }
       }
+    }
+  }
+  if constexpr (sizeof(T) == 4) {
+    const int variant = g_bwd_variant.load(std::memory_order_relaxed);
+    const int LP = d.L * d.P;
+    if (variant != 1 && vec_ok && d.D == 32 && LP <= kMaxLP && aligned16(loc) && aligned16(attn) &&
+        aligned16(gloc) && aligned16(gattn) && groups < (int64_t(1) << 31)) {
+      const Family fam = pick_family(variant, groups, d);
       if (fam == Family::kWide) {
         const unsigned grid = unsigned((groups + kWideThreads / 32 - 1) / (kWideThreads / 32));
         msda_bwd_wide_kernel<<<grid, kWideThreads, 0, st>>>(value, shapes, loc, attn, gout, gval, gloc, gattn, d.S, d.M,

@@ -20,6 +20,9 @@
 // exactly once (coalesced reads of sampling_loc / attn_weight) and parks it in shared memory; the backward
 // writes grad_attn / grad_loc back into the tap slots and streams them out coalesced at the end.
 // Semantics as in msda_d32.cuh (shifted window == the reference's zero padding for finite inputs).
+//
+// LG = lanes per group = 16-byte packs per head row: 8 for D = 32, 9 for the multi-frame geometry D = 36 (a warp then
+// carries three runs, lanes 27..31 shadow the last lane of run 2 with every store / reduction masked).
 #pragma once
 
 #include "msda_d32.cuh"
@@ -29,10 +32,10 @@ namespace msda {
 constexpr int kRunThreads = 128;
 constexpr int kRunHeads = 4;            // heads per unit (= warps per CTA)
 
-template <int R> __host__ __device__ constexpr int run_rows() { return 4 * R * kRunHeads; }   // (query, head) rows per unit
-__host__ __device__ inline int run_entries(int R, int LP) { return 4 * R * kRunHeads * LP + 4; }
-__host__ __device__ inline size_t fwd_run_smem_bytes(int R, int LP) { return size_t(run_entries(R, LP)) * (16 + 4); }
-__host__ __device__ inline size_t bwd_run_smem_bytes(int R, int LP) { return size_t(run_entries(R, LP)) * (16 + 8); }
+__host__ __device__ constexpr int run_runs(int LG) { return 32 / LG; }                          // runs per warp: 4 or 3
+__host__ __device__ inline int run_entries(int LG, int R, int LP) { return run_runs(LG) * R * kRunHeads * LP + 4; }
+__host__ __device__ inline size_t fwd_run_smem_bytes(int LG, int R, int LP) { return size_t(run_entries(LG, R, LP)) * (16 + 4); }
+__host__ __device__ inline size_t bwd_run_smem_bytes(int LG, int R, int LP) { return size_t(run_entries(LG, R, LP)) * (16 + 8); }
 
 // tap slot of (row, s): rows are (query-in-unit * 4 + head); every run's block is skewed by one slot so that the
 // four 8-lane groups of a warp (same head, same step, four runs) hit four different bank groups
@@ -55,24 +58,25 @@ __device__ __forceinline__ void red4v(float* p, const float4& g) {
 // ------------------------------------------------------------------------------------------------
 // Forward
 // ------------------------------------------------------------------------------------------------
-template <int R, int LP_CT>
+template <int LG, int R, int LP_CT>
 __global__ void __launch_bounds__(kRunThreads, 4)
 msda_fwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                     const float* __restrict__ loc, const float* __restrict__ attn, float* __restrict__ out,
                     int S, int M, int L, int Lq, int P, int qblocks) {
-  constexpr int D = 32, QB = 4 * R, ROWS = QB * kRunHeads;
+  constexpr int D = 4 * LG, RUNS = run_runs(LG), QB = RUNS * R, ROWS = QB * kRunHeads;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ LevelTable lv;
   __shared__ unsigned char lvl_of[kMaxLP];
 
   const int LP = LP_CT ? LP_CT : L * P;
-  const int entries = run_entries(R, LP);
+  const int entries = run_entries(LG, R, LP);
   float4* s_w = reinterpret_cast<float4*>(smem_raw);             // corner weights * attn
   int* s_o = reinterpret_cast<int*>(s_w + entries);               // element offset of the window's first corner
   const int stride = M * D;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int k = lane >> 3, j = lane & 7;
+  const bool live = lane < RUNS * LG;                             // (LG = 9: lanes 27..31 shadow lane 26)
+  const int k = live ? lane / LG : RUNS - 1, j = live ? lane - k * LG : LG - 1;
 
   const int hblocks = M / kRunHeads;
   const int unit = blockIdx.x;
@@ -176,7 +180,7 @@ msda_fwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int gq = q0 + k * R + r;
-    if (gq < Lq)
+    if (live && gq < Lq)
       *reinterpret_cast<float4*>(out + ((size_t(n) * Lq + gq) * M + m) * D + j * 4) = acc[r];
   }
 }
@@ -191,27 +195,69 @@ __device__ __forceinline__ int axis_code(float da, float db) { return da < 0.f ?
 __device__ __forceinline__ float code_da(int c) { return c == 0 ? -1.f : (c == 1 ? 1.f : 0.f); }
 __device__ __forceinline__ float code_db(int c) { return c == 0 ? 1.f : (c == 2 ? -1.f : 0.f); }
 
-template <int R, int LP_CT>
+// Sums the 12 per-lane partials of four steps over the LG lanes of every group: afterwards lanes j = 0, 2, 4, 6 of a
+// group hold (grad_attn, grad_loc.x, grad_loc.y) of step j >> 1.  LG = 8: transposing xor butterfly (12 shuffles);
+// LG = 9: lane 8 is folded into lanes 0..7 first (12 more), then the same butterfly with explicit partner lanes.
+template <int LG>
+__device__ __forceinline__ void reduce_steps(float (&part)[12], float (&r3)[3], int lane, int k, int j) {
+  int p4, p2, p1;
+  if (LG == 8) {
+    p4 = lane ^ 4; p2 = lane ^ 2; p1 = lane ^ 1;
+  } else {
+    const int base = k * LG;
+#pragma unroll
+    for (int c = 0; c < 12; ++c) {
+      const float v = __shfl_sync(0xffffffffu, part[c], base + 8);
+      if (j == (c & 7)) part[c] += v;
+    }
+    const int jj = j < 8 ? j : 0;                   // lane 8 (and the shadow lanes): harmless partners, result unused
+    p4 = base + (jj ^ 4); p2 = base + (jj ^ 2); p1 = base + (jj ^ 1);
+  }
+  float r6[6];
+  {
+    const bool hi = j & 4;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const float mine = hi ? part[6 + c] : part[c];
+      const float give = hi ? part[c] : part[6 + c];
+      r6[c] = mine + __shfl_sync(0xffffffffu, give, p4);
+    }
+  }
+  {
+    const bool hi = j & 2;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float mine = hi ? r6[3 + c] : r6[c];
+      const float give = hi ? r6[c] : r6[3 + c];
+      r3[c] = mine + __shfl_sync(0xffffffffu, give, p2);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) r3[c] += __shfl_sync(0xffffffffu, r3[c], p1);
+}
+
+template <int LG, int R, int LP_CT>
 __global__ void __launch_bounds__(kRunThreads, 4)
 msda_bwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                     const float* __restrict__ loc, const float* __restrict__ attn,
                     const float* __restrict__ grad_out, float* __restrict__ grad_value,
                     float* __restrict__ grad_loc, float* __restrict__ grad_attn,
                     int S, int M, int L, int Lq, int P, int qblocks) {
-  constexpr int D = 32, QB = 4 * R, ROWS = QB * kRunHeads;
+  constexpr int D = 4 * LG, RUNS = run_runs(LG), QB = RUNS * R, ROWS = QB * kRunHeads;
   static_assert(R % 4 == 0, "the lane butterfly reduces four steps at a time");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ LevelTable lv;
   __shared__ unsigned char lvl_of[kMaxLP];
 
   const int LP = LP_CT ? LP_CT : L * P;
-  const int entries = run_entries(R, LP);
+  const int entries = run_entries(LG, R, LP);
   float4* s_w = reinterpret_cast<float4*>(smem_raw);
   float2* s_ao = reinterpret_cast<float2*>(s_w + entries);
   const int stride = M * D;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int k = lane >> 3, j = lane & 7;
+  const bool live = lane < RUNS * LG;                             // shadow lanes: no reductions, no stores
+  const int k = live ? lane / LG : RUNS - 1, j = live ? lane - k * LG : LG - 1;
 
   const int hblocks = M / kRunHeads;
   const int unit = blockIdx.x;
@@ -260,7 +306,8 @@ msda_bwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     const int gq = q0 + k * R + r;
-    g[r] = gq < Lq ? ldg4(grad_out + ((size_t(n) * Lq + gq) * M + m) * D + j * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    g[r] = (live && gq < Lq) ? ldg4(grad_out + ((size_t(n) * Lq + gq) * M + m) * D + j * 4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
   for (int s = 0; s < LP; ++s) {
@@ -298,12 +345,12 @@ msda_bwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__
           const bool ldA = reload || (shift && !par);
           const bool ldB = reload || (shift && par);
           if (ldA) {
-            if ((unsigned(nzA) << 1) != 0) { red4v(gvb + oA, GA1); red4v(gvb + oA + rowpitch, GA3); }
+            if (live && (unsigned(nzA) << 1) != 0) { red4v(gvb + oA, GA1); red4v(gvb + oA + rowpitch, GA3); }
             GA1 = zero4; GA3 = zero4; nzA = 0;
             oA = reload ? o : o + stride;
           }
           if (ldB) {
-            if ((unsigned(nzB) << 1) != 0) { red4v(gvb + oB, GB1); red4v(gvb + oB + rowpitch, GB3); }
+            if (live && (unsigned(nzB) << 1) != 0) { red4v(gvb + oB, GB1); red4v(gvb + oB + rowpitch, GB3); }
             GB1 = zero4; GB3 = zero4; nzB = 0;
             oB = o + stride;
           }
@@ -334,7 +381,7 @@ msda_bwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__
         } else {
           // degenerate level: predicated taps on the fly (reference formulas, .cuh:96-163), direct reductions
           const int gq = q0 + k * R + r;
-          if (gq < Lq) {
+          if (live && gq < Lq) {
             const size_t sidx = ((size_t(n) * Lq + gq) * M + m) * LP + s;
             const float a = __ldg(attn + sidx);
             const Tap<float> t = make_tap<float>(__ldg(loc + 2 * sidx), __ldg(loc + 2 * sidx + 1), H, W, stride);
@@ -359,35 +406,15 @@ msda_bwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__
         part[3 * u + 1] = s_x;
         part[3 * u + 2] = s_y;
       }
-      // transposing butterfly over the 8 lanes: afterwards lane j holds the full sums of step u = j >> 1
-      float r6[6], r3[3];
-      {
-        const bool hi = j & 4;
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          const float mine = hi ? part[6 + c] : part[c];
-          const float give = hi ? part[c] : part[6 + c];
-          r6[c] = mine + __shfl_xor_sync(0xffffffffu, give, 4);
-        }
-      }
-      {
-        const bool hi = j & 2;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float mine = hi ? r6[3 + c] : r6[c];
-          const float give = hi ? r6[c] : r6[3 + c];
-          r3[c] = mine + __shfl_xor_sync(0xffffffffu, give, 2);
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) r3[c] += __shfl_xor_sync(0xffffffffu, r3[c], 1);
-      if (!(j & 1)) {
-        // the tap slot of (step, s) has been consumed by all 8 lanes: reuse it for the three gradients
+      float r3[3];
+      reduce_steps<LG>(part, r3, lane, k, j);
+      if (live && j < 8 && !(j & 1)) {
+        // the tap slot of (step, s) has been consumed by all lanes of the group: reuse it for the three gradients
         const int slot = run_slot<R>(row0 + (r0 + (j >> 1)) * kRunHeads, s, LP);
         s_w[slot] = make_float4(r3[0], r3[1], r3[2], 0.f);
       }
     }
-    if (fast) {
+    if (fast && live) {
       if ((unsigned(nzA) << 1) != 0) { red4v(gvb + oA, GA1); red4v(gvb + oA + rowpitch, GA3); }
       if ((unsigned(nzB) << 1) != 0) { red4v(gvb + oB, GB1); red4v(gvb + oB + rowpitch, GB3); }
     }
