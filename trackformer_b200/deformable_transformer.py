@@ -139,7 +139,10 @@ class DeformableTransformerDecoderLayer(nn.Module):
         # (every other decoder op is row-wise).
         qk = _add_pos(tgt, query_pos).transpose(0, 1)
         key_mask = query_attn_mask if padded_queries is None else padded_queries
-        sa = self.self_attn(qk, qk, tgt.transpose(0, 1), key_padding_mask=key_mask)[0].transpose(0, 1)
+        # need_weights=False: the averaged attention map is never used (the reference discards it too,
+        # deformable_transformer.py:368) and asking for it forces the unfused bmm / softmax / bmm path with ~25 small
+        # launches per layer and direction; without it the module runs one fused attention kernel
+        sa = self.self_attn(qk, qk, tgt.transpose(0, 1), key_padding_mask=key_mask, need_weights=False)[0].transpose(0, 1)
         tgt = add_dropout_layernorm(tgt, sa, self.dropout2, self.norm2)
         # deformable cross-attention into the encoder memory
         ca = self.cross_attn(_add_pos(tgt, query_pos), reference_points, src, src_spatial_shapes,
