@@ -24,6 +24,9 @@ run fused_loss  TFB200_FUSED_LOSS=1
 run tcgen05     TFB200_TCGEN05_LINEAR=1
 run tcgen05_f   TFB200_TCGEN05_LINEAR=1 TFB200_TCGEN05_PARTS=f
 run both        TFB200_FUSED_LOSS=1 TFB200_TCGEN05_LINEAR=1
+echo "=== reference classes on the same GPU: (a) on our extension (zero-edit drop-in), (b) on the reference's own CUDA kernels"
+timeout 600 python tools/ref_gpu_bench.py --msda ours --check --out gpurun_out/r2_ref_gpu_ours.json 2>&1 | tail -2 | cut -c1-400
+timeout 600 python tools/ref_gpu_bench.py --msda refcuda --out gpurun_out/r2_ref_gpu_refcuda.json 2>&1 | tail -2 | cut -c1-400
 echo "=== model parity (incl. the new full-size cases)"
 timeout 1500 python -m pytest tests/test_model_parity_gpu.py tests/test_tracker_gpu.py -q -s 2>&1 | grep -v "^$" | tail -40
 echo "=== ncu launch list of the step graph (kernel nodes)"
