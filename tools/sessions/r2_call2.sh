@@ -9,6 +9,7 @@ echo "=== opbench"
 timeout 900 python tools/opbench.py --cases c2_enc_init,c2_enc_smooth,c2_enc_model,c2_enc_uniform,c2_dec,c2_enc_init_n2,c2_dec_n2 \
    --variants 0,100,101,110,20 --bwd-variants 0,100,101,110,20 --iters 20 --out gpurun_out/r2_opbench_v1.json 2>&1 | cut -c1-230
 echo "=== tcgen05 GEMM (own timeout: a wrong barrier would hang)"
+timeout 300 python -m pytest tests/test_tf32_gemm_gpu.py -q -x 2>&1 | tail -6
 timeout 300 python tools/gemm_bench.py --iters 10 2>&1 | cut -c1-400 | tail -12
 echo "=== prep tests + fused loss / refine tests"
 timeout 900 python -m pytest tests/test_fused_loss_gpu.py tests/test_fused_bn_gpu.py tests/test_fused_norm_gpu.py tests/test_train_step_gpu.py -q 2>&1 | tail -8
