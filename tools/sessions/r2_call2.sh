@@ -4,15 +4,15 @@ set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader
 echo "=== op tests"
-timeout 1200 python -m pytest tests/test_msda_gpu.py -q -x 2>&1 | tail -8
+timeout 1200 python -m pytest tests/test_msda_gpu.py -q --maxfail=12 --tb=line 2>&1 | tail -30
 echo "=== opbench"
 timeout 900 python tools/opbench.py --cases c2_enc_init,c2_enc_smooth,c2_enc_model,c2_enc_uniform,c2_dec,c2_enc_init_n2,c2_dec_n2 \
    --variants 0,100,101,110,20 --bwd-variants 0,100,101,110,20 --iters 20 --out gpurun_out/r2_opbench_v1.json 2>&1 | cut -c1-230
 echo "=== tcgen05 GEMM (own timeout: a wrong barrier would hang)"
-timeout 300 python -m pytest tests/test_tf32_gemm_gpu.py -q -x 2>&1 | tail -6
+timeout 300 python -m pytest tests/test_tf32_gemm_gpu.py -q --maxfail=6 --tb=line 2>&1 | tail -14
 timeout 300 python tools/gemm_bench.py --iters 10 2>&1 | cut -c1-400 | tail -12
 echo "=== prep tests + fused loss / refine tests"
-timeout 900 python -m pytest tests/test_fused_loss_gpu.py tests/test_fused_bn_gpu.py tests/test_fused_norm_gpu.py tests/test_train_step_gpu.py -q 2>&1 | tail -8
+timeout 900 python -m pytest tests/test_fused_loss_gpu.py tests/test_fused_bn_gpu.py tests/test_fused_norm_gpu.py tests/test_train_step_gpu.py -q --tb=line 2>&1 | tail -16
 run() {
   local name=$1; shift
   env "$@" timeout 600 python bench.py --steps 40 --warmup 5 --no-cpu-baseline 2>gpurun_out/bench_r2_${name}.err | tee gpurun_out/bench_r2_${name}.json | cut -c1-170
@@ -29,7 +29,7 @@ echo "=== reference classes on the same GPU: (a) on our extension (zero-edit dro
 timeout 600 python tools/ref_gpu_bench.py --msda ours --check --out gpurun_out/r2_ref_gpu_ours.json 2>&1 | tail -2 | cut -c1-400
 timeout 600 python tools/ref_gpu_bench.py --msda refcuda --out gpurun_out/r2_ref_gpu_refcuda.json 2>&1 | tail -2 | cut -c1-400
 echo "=== model parity (incl. the new full-size cases)"
-timeout 1500 python -m pytest tests/test_model_parity_gpu.py tests/test_tracker_gpu.py -q -s 2>&1 | grep -v "^$" | tail -40
+timeout 1500 python -m pytest tests/test_model_parity_gpu.py tests/test_tracker_gpu.py -q -s --tb=line 2>&1 | grep -v "^$" | tail -60
 echo "=== ncu launch list of the step graph (kernel nodes)"
 timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -c 14000 --csv \
   --log-file gpurun_out/r2_launches_head.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
