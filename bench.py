@@ -19,6 +19,9 @@ Output: ONE JSON line on rank 0 (see the driver contract), with
   e2e       frames/s with the frame copied from pinned host memory and the loss read back every step
   roofline  the dominant own kernel (MSDeformAttn encoder backward), CUDA-event timed per launch inside the
             timed region; achieved = algorithmic bytes / mean launch time vs the measured HBM peak
+  roofline_dense / roofline_e2e   tensor-pipe and whole-step rooflines (lower bounds, see the notes in the line)
+  variable_gt   the same metric when the ground-truth box count changes every step (two-graph path)
+  parity_vs_reference_c2   measured max relative error of logits / boxes against the reference's C2 golden
   cpu_baseline  the reference's pure-PyTorch path (oracle/torch_ref.py driving the same host-side model on
             the host cores), rank 0, N=1 only, bounded sample
 `--impl reference` prints the CPU arm as the main line (rank 0 only; other ranks exit 0).
@@ -72,6 +75,62 @@ def make_targets(batch, device, seed):
         out.append({"boxes": torch.cat([cxcy, wh], 1).to(device),
                     "labels": torch.zeros(N_GT, dtype=torch.int64, device=device)})
     return out
+
+
+def tensor_peak(tf32: bool):
+    """Dense tensor-pipe denominator for the precision actually used: the driver-measured sustained bf16 cuBLAS rate
+    (the step is long, MEASURED_PEAKS.json) halved for TF32 (half the bf16 rate on this part); strict fp32 has no
+    tensor-pipe roofline."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    bf16 = 1400.0
+    src = "fallback 1.4 PFLOP/s bf16 sustained (B200_PROFILING.md)"
+    if os.path.exists(p):
+        try:
+            bf16 = float(json.load(open(p))["bf16_tflops_sustained"])
+            src = "MEASURED_PEAKS.json bf16_tflops_sustained"
+        except Exception:
+            pass
+    return (bf16 / 2 if tf32 else None), src + (" / 2 (TF32)" if tf32 else "")
+
+
+def dense_flops_per_step(step_fn):
+    """FLOPs of the dense contractions (convolutions, matmuls, attention products) of ONE training step, counted by
+    torch's FlopCounterMode over an eager step (forward + backward; the MSDeformAttn core is not a contraction)."""
+    import trackformer_b200.fused_linear as fl
+    own = fl._TCGEN05
+    fl._TCGEN05 = False                      # count the long-token Linears too (the own kernel is not an aten::mm)
+    try:
+        from torch.utils.flop_counter import FlopCounterMode
+        with FlopCounterMode(display=False) as fc:
+            step_fn()
+        return float(fc.get_total_flops())
+    except Exception:
+        return None
+    finally:
+        fl._TCGEN05 = own
+
+
+def golden_parity(dev):
+    """max relative error of pred_logits / pred_boxes on the C2 golden case (reference classes on CPU, recorded by
+    tests/golden/make_golden_model.py) under the dense-math setting of this run."""
+    try:
+        import numpy as np
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import model_fixtures as mf
+        from trackformer_b200.model_factory import build_model, default_args
+        gold = np.load(os.path.join(ROOT, "tests", "golden", "model_det_c2_800x1333.npz"))
+
+        def build(tracking, multi_frame, **kw):
+            torch.manual_seed(0)
+            m, c, _ = build_model(default_args(tracking, multi_frame, device=str(dev), **kw))
+            return m, c
+        res = mf.run_detection(build, [(800, 1333)], device=dev)
+        out = {}
+        for k in ("pred_logits", "pred_boxes"):
+            out[k] = float(np.abs(res[k] - gold[k]).max() / np.abs(gold[k]).max())
+        return out
+    except Exception as exc:
+        return {"error": repr(exc)}
 
 
 class ClockSampler:
@@ -283,11 +342,29 @@ def main():
     ms_e2e = timed(e2e_step, args.steps)
     e2e_value = bpg * world * args.steps / (ms_e2e / 1e3)
 
+    # (2b) the general path: ground-truth box counts that change every step (forward graph + sync-free loss + backward
+    #      graph instead of the single full-step graph, whose capture is tied to the box count)
+    var_targets = [make_targets(bpg, dev, 100 + i) for i in range(4)]
+    for i, tg in enumerate(var_targets):
+        for t in tg:
+            keep = N_GT - 1 - (i % 3)
+            t["boxes"], t["labels"] = t["boxes"][:keep].contiguous(), t["labels"][:keep].contiguous()
+    counter = [0]
+
+    def var_step():
+        counter[0] += 1
+        step(dev_frames, var_targets[counter[0] % len(var_targets)])
+    for _ in range(3):
+        var_step()
+    ms_var = timed(var_step, args.steps)
+    var_value = bpg * world * args.steps / (ms_var / 1e3)
+
     # (3) per-launch timing of the own kernels.  CUDA-graph replays cannot host per-kernel events, so the same
     #     step (same model, same inputs, same kernels) is replayed eagerly with every MSDeformAttn launch bracketed
     #     by CUDA events on the launching stream; the launch counter gives the kernels per step.
     probe = TrainStep(model, criterion, None, use_graphs=False)
     probe(dev_frames, targets)
+    dense_flops = dense_flops_per_step(lambda: probe(dev_frames, targets)) if rank == 0 else None
     sink = []
     msda_function.set_timing_sink(sink)
     launches0 = msda.launch_count()
@@ -351,6 +428,28 @@ def main():
             l1_roofline["kernels"][r["kernel"]] = {"gathered_bytes": gathered, "achieved_gbs": round(gbs, 1),
                                                    "frac": round(gbs / l1_peak, 4)}
     msda_ms = sum(r["total_ms_per_step"] for r in per_kernel)
+    msda_bytes = sum(r["alg_bytes"] * r["launches"] for r in per_kernel) / max(probe_steps, 1)
+
+    # tensor-pipe and end-to-end rooflines.  Dense time is bounded from above by "step minus MSDeformAttn"
+    # (it still contains every elementwise / normalisation / optimizer pass), so `achieved` is a LOWER bound.
+    ms_step = ms_total / args.steps
+    tc_peak, tc_src = tensor_peak(tf32)
+    roofline_dense = roofline_e2e = None
+    if dense_flops:
+        per_gpu_flops = dense_flops                                    # one rank's step
+        dense_ms = max(ms_step - msda_ms, 1e-6)
+        ach = per_gpu_flops / dense_ms / 1e9
+        roofline_dense = {"bound": "tensor", "flops_per_step": per_gpu_flops, "time_ms_upper_bound": round(dense_ms, 3),
+                          "achieved": round(ach, 1), "unit": "TFLOP/s", "peak": tc_peak, "peak_source": tc_src,
+                          "frac": round(ach / tc_peak, 4) if tc_peak else None,
+                          "note": "dense FLOPs (FlopCounterMode, fwd+bwd) / (step - MSDeformAttn time): lower bound"}
+        if tc_peak:
+            ideal_ms = msda_bytes / (peak * 1e6) + per_gpu_flops / (tc_peak * 1e9)
+            roofline_e2e = {"ideal_ms": round(ideal_ms, 3), "measured_ms": round(ms_step, 3),
+                            "frac": round(ideal_ms / ms_step, 4),
+                            "note": "(MSDeformAttn algorithmic bytes / HBM peak + dense FLOPs / tensor peak) / measured step; "
+                                    "elementwise, normalisation and optimizer traffic not credited (lower bound)"}
+    parity = golden_parity(dev) if world == 1 else None
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -367,9 +466,9 @@ def main():
         "metric": "frames/sec Deformable-DETR R50 800x1333 fwd+bwd", "value": value, "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": "tf32+f32" if tf32 else "f32", "data": "synthetic",
         "config": {"workload": workload, "global_batch": bpg * world, "parallelism": f"dp{world}",
-                   "dense_math": "TF32 tensor cores (cuDNN/cuBLAS), fp32 accumulate" if tf32 else "strict fp32",
+                   "dense_math": "TF32 tensor cores (cuDNN / cuBLAS / own tcgen05 Linear), fp32 accumulate" if tf32 else "strict fp32",
                    "msda_math": "fp32 (hand-written sm_100a kernels)", "dropout": 0.1,
                    "optimizer": "none" if args.no_optimizer else ("torch AdamW(fused)" if args.torch_adamw else "flat one-pass AdamW kernel, reference lr groups") + " + clip_grad_norm 0.1",
                    "execution": "eager" if args.no_graphs else
@@ -387,7 +486,12 @@ def main():
         "gpu_launches": int(launches) * world,
         "clocks": clocks,
         "roofline": roofline,
-        "l1_roofline": l1_roofline,
+        "roofline_dense": roofline_dense,
+        "roofline_e2e": roofline_e2e,
+        "variable_gt": {"value": var_value, "unit": "frames/s", "ms_per_step": ms_var / args.steps,
+                        "note": "ground-truth box count changes every step: forward graph + sync-free loss + backward graph"},
+        "parity_vs_reference_c2": parity,
+        "diagnostics": {"l1_gather_probe": l1_roofline},
         "msda_kernels": per_kernel,
         "msda_ms_per_step": round(msda_ms, 4),
         "cpu_baseline": cpu_baseline,
