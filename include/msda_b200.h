@@ -87,6 +87,20 @@ int msda_b200_backward_f64(const double* value, const int64_t* spatial_shapes,
  * Returns MSDA_E_UNSUPPORTED (nothing launched) unless fp32, D == 32, L <= 8, L*P <= 64, Lq == S == sum(H*W),
  * every H, W >= 2 and the buffers are 16-byte aligned -- callers then use msda_b200_forward_f32.
  * No reference counterpart (the reference has a single kernel for every call site).                         */
+/* ---- fused-prologue variant (module-level fusion) ------------------------------------------------------
+ * The sampling locations and attention weights of ops/modules/ms_deform_attn.py:69-79 are computed INSIDE the kernel:
+ *   proj [N][Lq][3*M*L*P]  the raw output of the module's [sampling_offsets | attention_weights] projections:
+ *                          [M][L][P][2] offsets followed by [M][L*P] logits (softmax over L*P per head in-kernel)
+ *   ref  [N][Lq][L][2]     reference points;  loc = ref + offset / spatial_shapes (divided as stored, like the reference)
+ * backward writes grad_proj (same layout: offset gradients, then the logit gradients through the softmax) and
+ * zero-fills + accumulates grad_value.  Domain: fp32, D = 32 or 36, M % 4 == 0, L*P == 16; MSDA_E_UNSUPPORTED otherwise
+ * (callers then materialise loc / attn and use msda_b200_forward_f32 / _backward_f32).                              */
+int msda_b200_forward_fused_f32(const float* value, const int64_t* spatial_shapes, const float* proj, const float* ref,
+                                float* output, int N, int S, int M, int D, int L, int Lq, int P, void* stream);
+int msda_b200_backward_fused_f32(const float* value, const int64_t* spatial_shapes, const float* proj, const float* ref,
+                                 const float* grad_output, float* grad_value, float* grad_proj, int N, int S, int M, int D,
+                                 int L, int Lq, int P, void* stream);
+
 int msda_b200_forward_enc_tiled_f32(const float* value, const int64_t* spatial_shapes_host,
                                     const float* sampling_loc, const float* attn_weight, float* output,
                                     int N, int S, int M, int D, int L, int Lq, int P, void* stream);

@@ -522,3 +522,41 @@ def test_run_kernels_d36_match_c_oracle(msda, dev, name, variant):
     np.testing.assert_allclose(gv.cpu().numpy(), ref_gv, rtol=F32["rtol"], atol=F32["atol"] * scale)
     np.testing.assert_allclose(ga.cpu().numpy(), ref_ga, **F32)
     np.testing.assert_allclose(gl.cpu().numpy(), ref_gl, rtol=F32["rtol"] * 5, atol=F32["atol"] * 50)
+
+
+@pytest.mark.parametrize("D", [32, 36])
+def test_fused_prologue_equals_module_chain(msda, dev, D):
+    """MSDeformAttnFusedFunction (softmax + location arithmetic in the kernel prologue) against the
+    materialising chain softmax -> locations -> MSDeformAttnFunction on the same projection, forward and both gradients"""
+    from trackformer_b200.msda_function import MSDeformAttnFunction, MSDeformAttnFusedFunction
+    hw = [(37, 53), (19, 27), (10, 14), (5, 7)]
+    g = torch.Generator().manual_seed(D)
+    shapes = torch.as_tensor(hw, dtype=torch.long)
+    S = int((shapes[:, 0] * shapes[:, 1]).sum())
+    N, M, L, P = 2, 8, 4, 4
+    value = torch.randn(N, S, M, D, generator=g).to(dev).requires_grad_(True)
+    proj = torch.randn(N, S, 3 * M * L * P, generator=g)
+    proj[..., :2 * M * L * P] *= 2.0
+    proj = proj.to(dev).requires_grad_(True)
+    refs = []
+    for (h, w) in hw:
+        ys, xs = torch.meshgrid(torch.arange(h) + 0.5, torch.arange(w) + 0.5, indexing="ij")
+        refs.append(torch.stack([xs.reshape(-1) / w, ys.reshape(-1) / h], -1))
+    ref = torch.cat(refs, 0)[None, :, None, :].expand(N, S, L, 2).contiguous().to(dev)
+    gout = torch.randn(N, S, M * D, generator=g).to(dev)
+    ts = shapes.to(dev)
+
+    out = MSDeformAttnFusedFunction.apply(value, ts, proj, ref, P)
+    out.backward(gout)
+    gv, gp = value.grad.clone(), proj.grad.clone()
+    value.grad = proj.grad = None
+
+    n_off = 2 * M * L * P
+    offsets = proj[..., :n_off].reshape(N, S, M, L, P, 2)
+    attn = torch.softmax(proj[..., n_off:].reshape(N, S, M, L * P), -1).view(N, S, M, L, P)
+    loc = ref[:, :, None, :, None, :] + offsets / ts.float()[None, None, None, :, None, :]      # (H, W) as stored
+    exp = MSDeformAttnFunction.apply(value, ts, loc, attn, 64)
+    exp.backward(gout)
+    torch.testing.assert_close(out, exp, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(gv, value.grad, rtol=1e-4, atol=1e-4 * float(value.grad.abs().max()))
+    torch.testing.assert_close(gp, proj.grad, rtol=2e-3, atol=2e-4 * float(proj.grad.abs().max()))

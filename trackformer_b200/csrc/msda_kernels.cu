@@ -635,6 +635,68 @@ int msda_b200_backward_f64(const double* value, const int64_t* spatial_shapes, c
                                cudaStream_t(stream));
 }
 
+// ---- fused-prologue entry points: sampling locations / attention weights are computed inside the kernel from the
+//      module's raw [offsets | logits] projection and the reference points (ops/modules/ms_deform_attn.py:69-79) and
+//      never written to HBM.  Domain: fp32, D = 32 or 36, M % 4 == 0, L * P == 16, 2-d reference points.
+static int fused_domain(const Dims& d, const void* a, const void* b, const void* c, const void* e) {
+  if (int rc = check_dims(d)) return rc;
+  if ((d.D != 32 && d.D != 36) || d.M % kRunHeads != 0 || d.L * d.P != 16 || d.N < 1 || d.Lq < 1) return MSDA_E_UNSUPPORTED;
+  if (!aligned16(a) || !aligned16(b) || !aligned16(c) || !aligned16(e)) return MSDA_E_UNSUPPORTED;
+  return 0;
+}
+
+int msda_b200_forward_fused_f32(const float* value, const int64_t* spatial_shapes, const float* proj, const float* ref,
+                                float* output, int N, int S, int M, int D, int L, int Lq, int P, void* stream) {
+  const Dims d{N, S, M, D, L, Lq, P};
+  if (!value || !spatial_shapes || !proj || !ref || !output) return MSDA_E_NULLPTR;
+  if (int rc = fused_domain(d, value, proj, ref, output)) return rc;
+  cudaStream_t st = cudaStream_t(stream);
+  const int LG = D / 4, R = 8, QB = run_runs(LG) * R;
+  const int qblocks = (Lq + QB - 1) / QB;
+  const int64_t units = int64_t(N) * qblocks * (M / kRunHeads);
+  if (units >= (int64_t(1) << 31)) return MSDA_E_TOO_LARGE;
+  const size_t smem = fwd_run_smem_bytes(LG, R, 16);
+  if (LG == 8) {
+    MSDA_ENSURE_SMEM((msda_fwd_run_kernel<8, 8, 16, true>), smem);
+    msda_fwd_run_kernel<8, 8, 16, true><<<unsigned(units), kRunThreads, smem, st>>>(value, spatial_shapes, proj, ref, output, S,
+                                                                                   M, L, Lq, P, qblocks);
+  } else {
+    MSDA_ENSURE_SMEM((msda_fwd_run_kernel<9, 8, 16, true>), smem);
+    msda_fwd_run_kernel<9, 8, 16, true><<<unsigned(units), kRunThreads, smem, st>>>(value, spatial_shapes, proj, ref, output, S,
+                                                                                   M, L, Lq, P, qblocks);
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+
+int msda_b200_backward_fused_f32(const float* value, const int64_t* spatial_shapes, const float* proj, const float* ref,
+                                 const float* grad_output, float* grad_value, float* grad_proj, int N, int S, int M, int D,
+                                 int L, int Lq, int P, void* stream) {
+  const Dims d{N, S, M, D, L, Lq, P};
+  if (!value || !spatial_shapes || !proj || !ref || !grad_output || !grad_value || !grad_proj) return MSDA_E_NULLPTR;
+  if (int rc = fused_domain(d, value, proj, ref, grad_output)) return rc;
+  if (!aligned16(grad_value) || !aligned16(grad_proj)) return MSDA_E_UNSUPPORTED;
+  cudaStream_t st = cudaStream_t(stream);
+  cudaError_t e = cudaMemsetAsync(grad_value, 0, sizeof(float) * size_t(N) * S * M * D, st);
+  if (e != cudaSuccess) return int(e);
+  const int LG = D / 4, R = 8, QB = run_runs(LG) * R;
+  const int qblocks = (Lq + QB - 1) / QB;
+  const int64_t units = int64_t(N) * qblocks * (M / kRunHeads);
+  if (units >= (int64_t(1) << 31)) return MSDA_E_TOO_LARGE;
+  const size_t smem = bwd_run_smem_bytes(LG, R, 16);
+  if (LG == 8) {
+    MSDA_ENSURE_SMEM((msda_bwd_run_kernel<8, 8, 16, true>), smem);
+    msda_bwd_run_kernel<8, 8, 16, true><<<unsigned(units), kRunThreads, smem, st>>>(
+        value, spatial_shapes, proj, ref, grad_output, grad_value, grad_proj, nullptr, S, M, L, Lq, P, qblocks);
+  } else {
+    MSDA_ENSURE_SMEM((msda_bwd_run_kernel<9, 8, 16, true>), smem);
+    msda_bwd_run_kernel<9, 8, 16, true><<<unsigned(units), kRunThreads, smem, st>>>(
+        value, spatial_shapes, proj, ref, grad_output, grad_value, grad_proj, nullptr, S, M, L, Lq, P, qblocks);
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+
 int msda_b200_forward_enc_tiled_f32(const float* value, const int64_t* spatial_shapes_host, const float* sampling_loc,
                                     const float* attn_weight, float* output, int N, int S, int M, int D, int L,
                                     int Lq, int P, void* stream) {

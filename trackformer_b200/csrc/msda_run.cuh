@@ -55,10 +55,43 @@ __device__ __forceinline__ void red4v(float* p, const float4& g) {
                : "memory");
 }
 
+// One sample's normalised location and attention weight.
+//   PREP = false: read from sampling_loc / attn_weight (the reference's operands).
+//   PREP = true : computed from the module's raw projection, never materialised (ops/modules/ms_deform_attn.py:69-79):
+//                 `a` = the row [n, q] of the [offsets | logits] GEMM ([M][LP][2] offsets, then [M][LP] logits),
+//                 `b` = reference points [n, q][L][2];  loc = ref + offset / (H, W) -- the reference divides the (x, y)
+//                 offset by spatial_shapes AS STORED, i.e. by (H, W) -- and attn = softmax of the LP logits of the head,
+//                 reduced over the LP consecutive lanes that hold them (LP = 16).
+template <bool PREP, int LPC>
+__device__ __forceinline__ void run_sample(const float* __restrict__ a, const float* __restrict__ b, size_t nq, int m, int s,
+                                           int l, int M, int L, int LP, int H, int W, float& x, float& y, float& w) {
+  if (!PREP) {
+    const size_t sidx = (nq * M + m) * LP + s;
+    const float2 xy = __ldg(reinterpret_cast<const float2*>(a) + sidx);
+    x = xy.x; y = xy.y;
+    w = __ldg(b + sidx);
+  } else {
+    const float* prow = a + nq * size_t(3 * M * LPC);
+    const float2 off = __ldg(reinterpret_cast<const float2*>(prow) + m * LPC + s);
+    const float logit = __ldg(prow + 2 * M * LPC + m * LPC + s);
+    float mx = logit;
+#pragma unroll
+    for (int o = LPC / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e = expf(logit - mx);
+    float sum = e;
+#pragma unroll
+    for (int o = LPC / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    w = e / sum;
+    const float2 r = __ldg(reinterpret_cast<const float2*>(b) + nq * L + l);
+    x = r.x + off.x / float(H);
+    y = r.y + off.y / float(W);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Forward
 // ------------------------------------------------------------------------------------------------
-template <int LG, int R, int LP_CT>
+template <int LG, int R, int LP_CT, bool PREP = false>
 __global__ void __launch_bounds__(kRunThreads, 4)
 msda_fwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                     const float* __restrict__ loc, const float* __restrict__ attn, float* __restrict__ out,
@@ -88,7 +121,9 @@ msda_fwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__
   load_level_table(lv, lvl_of, shapes, L, P);
   __syncthreads();
 
-  // ---- prologue: one tap per (row, sample), read coalesced
+  // ---- prologue: one tap per (row, sample), read coalesced.  Degenerate levels (a single row or column) keep the raw
+  //      (x, y, attn) in the slot instead; the main loop builds their predicated taps on the fly.
+  static_assert(!PREP || LP_CT == 16, "the fused sampling prologue reduces over 16 consecutive lanes");
   for (int i = tid; i < ROWS * LP; i += kRunThreads) {
     const int row = i / LP, s = i - row * LP;
     const int gq = q0 + (row >> 2);
@@ -96,18 +131,22 @@ msda_fwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__
     const int H = lv.H[l], W = lv.W[l];
     float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
     int o = lv.start[l] * stride;
-    if (gq < Lq && H >= 2 && W >= 2) {
-      const size_t sidx = ((size_t(n) * Lq + gq) * M + hb * kRunHeads + (row & 3)) * LP + s;
-      const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + sidx);
-      const float a = __ldg(attn + sidx);
-      const float x = xy.x * float(W) - 0.5f, y = xy.y * float(H) - 0.5f;
-      if (y > -1.f && x > -1.f && y < float(H) && x < float(W)) {
-        int xb, yb;
-        float wxa, wxb, wya, wyb, d0, d1;
-        axis_window(x, W, xb, wxa, wxb, d0, d1);
-        axis_window(y, H, yb, wya, wyb, d0, d1);
-        w = make_float4(wya * wxa * a, wya * wxb * a, wyb * wxa * a, wyb * wxb * a);
-        o += (yb * W + xb) * stride;
+    float lx, ly, a;
+    run_sample<PREP, LP_CT ? LP_CT : 2>(loc, attn, size_t(n) * Lq + min(gq, Lq - 1), hb * kRunHeads + (row & 3), s, l, M, L,
+                                        LP, H, W, lx, ly, a);
+    if (gq < Lq) {
+      if (H >= 2 && W >= 2) {
+        const float x = lx * float(W) - 0.5f, y = ly * float(H) - 0.5f;
+        if (y > -1.f && x > -1.f && y < float(H) && x < float(W)) {
+          int xb, yb;
+          float wxa, wxb, wya, wyb, d0, d1;
+          axis_window(x, W, xb, wxa, wxb, d0, d1);
+          axis_window(y, H, yb, wya, wyb, d0, d1);
+          w = make_float4(wya * wxa * a, wya * wxb * a, wyb * wxa * a, wyb * wxb * a);
+          o += (yb * W + xb) * stride;
+        }
+      } else {
+        w = make_float4(lx, ly, a, 0.f);
       }
     }
     const int slot = run_slot<R>(row, s, LP);
@@ -158,16 +197,16 @@ msda_fwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__
         fma4(acc[r], par ? w.z : w.w, B3);
       }
     } else {
-      // degenerate level (a single row or column): predicated taps computed on the fly
+      // degenerate level (a single row or column): predicated taps built from the raw (x, y, attn) in the slot
       const float* vl = vb + size_t(lv.start[l]) * stride;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int gq = q0 + k * R + r;
         if (gq >= Lq) continue;
-        const size_t sidx = ((size_t(n) * Lq + gq) * M + m) * LP + s;
-        const Tap<float> t = make_tap<float>(__ldg(loc + 2 * sidx), __ldg(loc + 2 * sidx + 1), H, W, stride);
+        const float4 raw = s_w[run_slot<R>(row0 + r * kRunHeads, s, LP)];
+        const Tap<float> t = make_tap<float>(raw.x, raw.y, H, W, stride);
         if (!t.live) continue;
-        const float a = __ldg(attn + sidx);
+        const float a = raw.z;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         fma4(acc[r], t.w1 * a, t.k1 ? ldg4(vl + t.o1) : z);
         fma4(acc[r], t.w2 * a, t.k2 ? ldg4(vl + t.o2) : z);
@@ -236,7 +275,10 @@ __device__ __forceinline__ void reduce_steps(float (&part)[12], float (&r3)[3], 
   for (int c = 0; c < 3; ++c) r3[c] += __shfl_sync(0xffffffffu, r3[c], p1);
 }
 
-template <int LG, int R, int LP_CT>
+// PREP = true: `loc` / `attn` are the raw projection / reference points (see run_sample) and `grad_loc` receives the
+// gradient of the PROJECTION row ([M][LP][2] offset gradients, then [M][LP] logit gradients = softmax backward);
+// `grad_attn` is unused.
+template <int LG, int R, int LP_CT, bool PREP = false>
 __global__ void __launch_bounds__(kRunThreads, 4)
 msda_bwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                     const float* __restrict__ loc, const float* __restrict__ attn,
@@ -269,19 +311,21 @@ msda_bwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__
   load_level_table(lv, lvl_of, shapes, L, P);
   __syncthreads();
 
+  static_assert(!PREP || LP_CT == 16, "the fused sampling prologue reduces over 16 consecutive lanes");
   for (int i = tid; i < ROWS * LP; i += kRunThreads) {
     const int row = i / LP, s = i - row * LP;
     const int gq = q0 + (row >> 2);
     const int l = lvl_of[s];
     const int H = lv.H[l], W = lv.W[l];
     float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-    float a = 0.f;
     int o = lv.start[l] * stride + 15;                      // dead: codes (3, 3)
-    if (gq < Lq && H >= 2 && W >= 2) {
-      const size_t sidx = ((size_t(n) * Lq + gq) * M + hb * kRunHeads + (row & 3)) * LP + s;
-      const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + sidx);
-      a = __ldg(attn + sidx);
-      const float x = xy.x * float(W) - 0.5f, y = xy.y * float(H) - 0.5f;
+    float lx, ly, a;
+    run_sample<PREP, LP_CT ? LP_CT : 2>(loc, attn, size_t(n) * Lq + min(gq, Lq - 1), hb * kRunHeads + (row & 3), s, l, M, L,
+                                        LP, H, W, lx, ly, a);
+    if (gq >= Lq) {
+      a = 0.f;
+    } else if (H >= 2 && W >= 2) {
+      const float x = lx * float(W) - 0.5f, y = ly * float(H) - 0.5f;
       if (y > -1.f && x > -1.f && y < float(H) && x < float(W)) {
         int xb, yb;
         float dxa, dxb, dya, dyb;
@@ -289,6 +333,8 @@ msda_bwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__
         axis_window(y, H, yb, w.z, w.w, dya, dyb);
         o = (lv.start[l] + yb * W + xb) * stride + axis_code(dxa, dxb) + 4 * axis_code(dya, dyb);
       }
+    } else {
+      w = make_float4(lx, ly, 0.f, 0.f);                   // degenerate level: raw location, taps on the fly
     }
     const int slot = run_slot<R>(row, s, LP);
     s_w[slot] = w;
@@ -382,9 +428,10 @@ msda_bwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__
           // degenerate level: predicated taps on the fly (reference formulas, .cuh:96-163), direct reductions
           const int gq = q0 + k * R + r;
           if (live && gq < Lq) {
-            const size_t sidx = ((size_t(n) * Lq + gq) * M + m) * LP + s;
-            const float a = __ldg(attn + sidx);
-            const Tap<float> t = make_tap<float>(__ldg(loc + 2 * sidx), __ldg(loc + 2 * sidx + 1), H, W, stride);
+            const int slot = run_slot<R>(row0 + r * kRunHeads, s, LP);
+            const float4 raw = s_w[slot];
+            const float a = s_ao[slot].x;
+            const Tap<float> t = make_tap<float>(raw.x, raw.y, H, W, stride);
             if (t.live) {
               const size_t lofs = size_t(lv.start[l]) * stride;
               const float4 v1 = t.k1 ? ldg4(vb + lofs + t.o1) : zero4, v2 = t.k2 ? ldg4(vb + lofs + t.o2) : zero4;
@@ -421,15 +468,31 @@ msda_bwd_run_kernel(const float* __restrict__ value, const int64_t* __restrict__
   }
   __syncthreads();
 
-  // ---- stream grad_attn / grad_loc out of the tap slots, coalesced
+  // ---- stream the gradients out of the tap slots, coalesced
   for (int i = tid; i < ROWS * LP; i += kRunThreads) {
     const int row = i / LP, s = i - row * LP;
     const int gq = q0 + (row >> 2);
-    if (gq >= Lq) continue;
-    const size_t sidx = ((size_t(n) * Lq + gq) * M + hb * kRunHeads + (row & 3)) * LP + s;
-    const float4 r = s_w[run_slot<R>(row, s, LP)];
-    grad_attn[sidx] = r.x;
-    *reinterpret_cast<float2*>(grad_loc + 2 * sidx) = make_float2(r.y, r.z);
+    const int slot = run_slot<R>(row, s, LP);
+    const float4 r = s_w[slot];
+    if (!PREP) {
+      if (gq >= Lq) continue;
+      const size_t sidx = ((size_t(n) * Lq + gq) * M + hb * kRunHeads + (row & 3)) * LP + s;
+      grad_attn[sidx] = r.x;
+      *reinterpret_cast<float2*>(grad_loc + 2 * sidx) = make_float2(r.y, r.z);
+    } else {
+      // projection gradient: offsets via d(loc)/d(off) = 1 / (H, W); logits via the softmax Jacobian
+      // a * (g - sum_s a_s g_s), the sum taken over the LP consecutive lanes of the head (all lanes take part)
+      const float a = s_ao[slot].x;
+      float dot = a * r.x;
+#pragma unroll
+      for (int o = (LP_CT ? LP_CT : 2) / 2; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+      if (gq >= Lq) continue;
+      const int l = lvl_of[s];
+      const int mm = hb * kRunHeads + (row & 3);
+      float* grow = grad_loc + (size_t(n) * Lq + gq) * size_t(3 * M * LP);
+      reinterpret_cast<float2*>(grow)[mm * LP + s] = make_float2(r.y / float(lv.H[l]), r.z / float(lv.W[l]));
+      grow[2 * M * LP + mm * LP + s] = a * (r.x - dot);
+    }
   }
 }
 

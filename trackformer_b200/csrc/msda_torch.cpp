@@ -133,6 +133,41 @@ std::vector<at::Tensor> ms_deform_attn_backward(const at::Tensor& value, const a
 
 // Encoder self-attention (queries == pixels): tiled kernel when the geometry allows, the general kernel otherwise.
 // `hw` is the host copy of spatial_shapes ([H0, W0, H1, W1, ...]) the caller already has.
+// fused-prologue variant: proj [N, Lq, 3*M*L*P] (raw [offsets | logits]), ref [N, Lq, L, 2]
+at::Tensor ms_deform_attn_forward_fused(const at::Tensor& value, const at::Tensor& spatial_shapes, const at::Tensor& proj,
+                                        const at::Tensor& ref, int64_t n_points) {
+  TORCH_CHECK(value.is_cuda() && proj.is_cuda() && ref.is_cuda() && spatial_shapes.is_cuda(), "Not implemented on the CPU");
+  TORCH_CHECK(value.scalar_type() == at::kFloat && proj.scalar_type() == at::kFloat && ref.scalar_type() == at::kFloat &&
+              spatial_shapes.scalar_type() == at::kLong && value.dim() == 4 && proj.dim() == 3 && ref.dim() == 4 &&
+              ref.size(3) == 2, "ms_deform_attn_forward_fused: dtypes / ranks");
+  const at::Tensor v = value.contiguous(), pr = proj.contiguous(), rf = ref.contiguous(), sh = spatial_shapes.contiguous();
+  const int64_t N = v.size(0), S = v.size(1), M = v.size(2), D = v.size(3), L = sh.size(0), Lq = pr.size(1), P = n_points;
+  TORCH_CHECK(pr.size(0) == N && pr.size(2) == 3 * M * L * P && rf.size(0) == N && rf.size(1) == Lq && rf.size(2) == L,
+              "ms_deform_attn_forward_fused: shapes");
+  const c10::cuda::CUDAGuard guard(value.device());
+  at::Tensor out = at::empty({N, Lq, M * D}, v.options());
+  const int rc = msda_b200_forward_fused_f32(v.data_ptr<float>(), sh.data_ptr<int64_t>(), pr.data_ptr<float>(), rf.data_ptr<float>(),
+                                             out.data_ptr<float>(), int(N), int(S), int(M), int(D), int(L), int(Lq), int(P),
+                                             c10::cuda::getCurrentCUDAStream().stream());
+  raise_on_error(rc, "ms_deform_attn_forward_fused");
+  return out;
+}
+
+std::vector<at::Tensor> ms_deform_attn_backward_fused(const at::Tensor& value, const at::Tensor& spatial_shapes,
+                                                      const at::Tensor& proj, const at::Tensor& ref, const at::Tensor& grad_output,
+                                                      int64_t n_points) {
+  const at::Tensor v = value.contiguous(), pr = proj.contiguous(), rf = ref.contiguous(), sh = spatial_shapes.contiguous();
+  const at::Tensor go = grad_output.contiguous();
+  const int64_t N = v.size(0), S = v.size(1), M = v.size(2), D = v.size(3), L = sh.size(0), Lq = pr.size(1), P = n_points;
+  const c10::cuda::CUDAGuard guard(value.device());
+  at::Tensor gv = at::empty_like(v), gp = at::empty_like(pr);
+  const int rc = msda_b200_backward_fused_f32(v.data_ptr<float>(), sh.data_ptr<int64_t>(), pr.data_ptr<float>(), rf.data_ptr<float>(),
+                                              go.data_ptr<float>(), gv.data_ptr<float>(), gp.data_ptr<float>(), int(N), int(S),
+                                              int(M), int(D), int(L), int(Lq), int(P), c10::cuda::getCurrentCUDAStream().stream());
+  raise_on_error(rc, "ms_deform_attn_backward_fused");
+  return {gv, gp};
+}
+
 at::Tensor ms_deform_attn_forward_enc(const at::Tensor& value, const at::Tensor& spatial_shapes,
                                       const at::Tensor& sampling_loc, const at::Tensor& attn_weight,
                                       const std::vector<int64_t>& hw, const int64_t im2col_step) {
@@ -583,6 +618,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("launch_count", []() { return msda_b200_launch_count(); });
   m.def("set_variant", [](int f, int b) { msda_b200_set_variant(f, b); });
   m.def("ms_deform_attn_forward_enc", &ms_deform_attn_forward_enc);
+  m.def("ms_deform_attn_forward_fused", &ms_deform_attn_forward_fused);
+  m.def("ms_deform_attn_backward_fused", &ms_deform_attn_backward_fused);
   m.def("add_dropout_layernorm_forward", &add_dropout_layernorm_forward);
   m.def("add_dropout_layernorm_backward", &add_dropout_layernorm_backward);
   m.def("add_dropout_layernorm_seeded_forward", &add_dropout_layernorm_seeded_forward);

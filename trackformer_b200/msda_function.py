@@ -97,3 +97,25 @@ def ms_deform_attn(value: torch.Tensor, spatial_shapes: torch.Tensor, sampling_l
                    attention_weights: torch.Tensor, im2col_step: int = 64) -> torch.Tensor:
     """Functional form: ``[N,S,M,D] x [L,2] x [N,Lq,M,L,P,2] x [N,Lq,M,L,P] -> [N,Lq,M*D]``."""
     return MSDeformAttnFunction.apply(value, spatial_shapes, sampling_locations, attention_weights, im2col_step)
+
+
+class MSDeformAttnFusedFunction(Function):
+    """The core op with the module's location / softmax arithmetic folded into the kernel prologue:
+    ``proj`` is the raw output of the [sampling_offsets | attention_weights] projections, ``reference_points``
+    [N, Lq, L, 2]; sampling locations and attention weights are never materialised (ops/modules/ms_deform_attn.py:69-79
+    + :86-87 in one launch per direction).  Gradients for ``value`` and ``proj``."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, proj, reference_points, n_points):
+        msda = ext.load()
+        ctx.n_points = int(n_points)
+        out = msda.ms_deform_attn_forward_fused(value, value_spatial_shapes, proj, reference_points, ctx.n_points)
+        ctx.save_for_backward(value, value_spatial_shapes, proj, reference_points)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, proj, ref = ctx.saved_tensors
+        gv, gp = ext.load().ms_deform_attn_backward_fused(value, shapes, proj, ref, grad_output.contiguous(), ctx.n_points)
+        return gv, None, gp, None, None

@@ -21,9 +21,11 @@ import torch.nn.functional as F
 from torch import nn
 
 from .fused_linear import linear as fused_linear
-from .msda_function import MSDeformAttnEncFunction, MSDeformAttnFunction
+from .msda_function import MSDeformAttnEncFunction, MSDeformAttnFunction, MSDeformAttnFusedFunction
 
 _TILED_ENC = os.environ.get("TFB200_TILED_ENC", "0") == "1"
+# fold sampling_prep into the MSDeformAttn kernels (csrc/msda_run.cuh PREP variants); off until validated on a B200
+_FUSED_PREP = os.environ.get("TFB200_FUSED_PREP", "0") != "0"
 
 # the 8 compass directions the reference seeds the per-head offset bias with (ms_deform_attn.py:36)
 _COMPASS = ((-1, -1), (-1, 0), (-1, 1), (0, -1), (0, 1), (1, -1), (1, 0), (1, 1))
@@ -134,6 +136,14 @@ class MSDeformAttn(nn.Module):
         proj = fused_linear(query, torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0),
                             torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0))
         lp = levels * points
+        d_head = self.d_model // heads
+        if (_FUSED_PREP and proj.is_cuda and proj.dtype == torch.float32 and query_attn_mask is None
+                and not reference_points.requires_grad and reference_points.shape[-1] == 2 and lp == 16
+                and d_head in (32, 36) and heads % 4 == 0 and n * len_q * heads > 32768 and len_q >= 2048):
+            # encoder-sized call: softmax + location arithmetic inside the gather kernel's prologue, sampling locations
+            # and attention weights never touch HBM (ms_deform_attn.py:69-87 as one launch per direction)
+            out = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, proj, reference_points, points)
+            return fused_linear(out, self.output_proj.weight, self.output_proj.bias)
         fusable = (proj.is_cuda and proj.dtype == torch.float32 and query_attn_mask is None
                    and not reference_points.requires_grad and reference_points.shape[-1] in (2, 4)
                    and lp in (4, 8, 16, 32) and (heads * lp) % 32 == 0)
