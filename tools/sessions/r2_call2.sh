@@ -23,8 +23,8 @@ run no_gather   TFB200_FUSED_BN=1 TFB200_GATHER_GRADS=0 TFB200_LN_SEEDED=1
 run no_seeded   TFB200_FUSED_BN=1 TFB200_GATHER_GRADS=1 TFB200_LN_SEEDED=0
 run fused_loss  TFB200_FUSED_LOSS=1
 run tcgen05     TFB200_TCGEN05_LINEAR=1
-run tcgen05_f   TFB200_TCGEN05_LINEAR=1 TFB200_TCGEN05_PARTS=f
-run both        TFB200_FUSED_LOSS=1 TFB200_TCGEN05_LINEAR=1
+run fused_prep  TFB200_FUSED_PREP=1
+run all_new     TFB200_FUSED_LOSS=1 TFB200_TCGEN05_LINEAR=1 TFB200_FUSED_PREP=1
 echo "=== reference classes on the same GPU: (a) on our extension (zero-edit drop-in), (b) on the reference's own CUDA kernels"
 timeout 600 python tools/ref_gpu_bench.py --msda ours --check --out gpurun_out/r2_ref_gpu_ours.json 2>&1 | tail -2 | cut -c1-400
 timeout 600 python tools/ref_gpu_bench.py --msda refcuda --out gpurun_out/r2_ref_gpu_refcuda.json 2>&1 | tail -2 | cut -c1-400
