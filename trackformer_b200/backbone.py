@@ -74,7 +74,9 @@ def _resize_mask(mask: torch.Tensor, size) -> torch.Tensor:
         key = (int(mask.shape[0]), size, mask.device)
         hit = _DENSE_MASKS.get(key)
         if hit is None:
-            hit = torch.zeros((mask.shape[0],) + size, dtype=torch.bool, device=mask.device)
+            # an expanded single element: read-only by construction (an in-place write into it raises), so a caller
+            # cannot corrupt the mask every other dense batch of this shape shares
+            hit = torch.zeros((1, 1, 1), dtype=torch.bool, device=mask.device).expand((mask.shape[0],) + size)
             hit._no_padding = True
             _DENSE_MASKS[key] = hit
         return hit
@@ -185,9 +187,13 @@ class Joiner(nn.Sequential):
         self.num_channels = backbone.num_channels
 
     def forward(self, tensor_list: NestedTensor):
-        if tensor_list.mask is not None and not hasattr(tensor_list.mask, "_no_padding"):
-            # one host sync per frame; lets every level reuse cached position encodings
-            tensor_list.mask._no_padding = not bool(tensor_list.mask.any())
+        mask = tensor_list.mask
+        if mask is not None and (not hasattr(mask, "_no_padding")
+                                 or getattr(mask, "_no_padding_version", mask._version) != mask._version):
+            # one host sync per frame; lets every level reuse cached position encodings.  The answer is tied to the
+            # tensor's version counter: a caller that writes padding into a reused mask buffer gets it re-evaluated.
+            mask._no_padding = not bool(mask.any())
+            mask._no_padding_version = mask._version
         feats = self[0](tensor_list)
         out: List[NestedTensor] = []
         pos = []

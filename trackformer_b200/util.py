@@ -41,6 +41,7 @@ def nested_tensor_from_tensor_list(images: Sequence[Tensor]) -> NestedTensor:
         b, _, h, w = images.shape
         mask = torch.zeros((b, h, w), dtype=torch.bool, device=images.device)
         mask._no_padding = True                           # known without looking at the data (no host sync)
+        mask._no_padding_version = mask._version          # ... for as long as nobody writes into it (backbone.Joiner)
         return NestedTensor(images, mask)
     first = images[0]
     if first.ndim != 3:
