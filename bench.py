@@ -326,6 +326,16 @@ def main():
     for _ in range(warm):
         step(dev_frames, targets)
 
+    if os.environ.get("TFB200_PROFILE_STEP") == "1":
+        # profiling aid (never a bench value): exactly ONE replayed step between cudaProfilerStart/Stop, for
+        #   ncu --profile-from-start off --graph-profiling node --metrics gpu__time_duration.sum ... python bench.py
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        step(dev_frames, targets)
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        return
+
     # (1) device-resident throughput
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:

@@ -94,7 +94,8 @@ GRAD_KEYS = (
 # ``build(tracking, multi_frame, **overrides)`` must return (model, criterion) on ``device``.
 # ---------------------------------------------------------------------------------------------
 def _to_np(x):
-    return x.detach().cpu().numpy()
+    # a COPY: on the CPU `.numpy()` aliases the tensor, and the optimizer leg clips / updates gradients and weights in place
+    return x.detach().cpu().numpy().copy()
 
 
 def run_detection(build, sizes, device="cpu", seed=0, **overrides):

@@ -24,6 +24,17 @@ F32 = dict(rtol=1e-4, atol=1e-4)     # O(1) data, 16..64-term fp32 dot products 
 F64 = dict(rtol=1e-10, atol=1e-12)
 
 
+def assert_close_but_for_ties(actual, desired, rtol, atol, max_bad=4, err_msg=""):
+    """assert_allclose that forgives a handful of elements.  grad_sampling_loc is DISCONTINUOUS where a sampling
+    coordinate lands exactly on a pixel boundary: `loc * W - 0.5` is one fused multiply-add on the GPU (as in the
+    reference's CUDA kernel, compiled with nvcc's default -fmad) but two roundings in the C oracle, so a sample that
+    sits on the boundary to the last bit may take the other cell -- a different, equally valid one-sided derivative.
+    With 11 M samples per full-size call that happens to about one element."""
+    bad = ~np.isclose(actual, desired, rtol=rtol, atol=atol)
+    if int(bad.sum()) > max_bad:
+        np.testing.assert_allclose(actual, desired, rtol=rtol, atol=atol, err_msg=err_msg)
+
+
 def tol(dt):
     return F32 if dt in (np.float32, torch.float32) else F64
 
@@ -370,6 +381,7 @@ TILE_CASES = {
     "wide_offsets": (1, 8, [(40, 56), (20, 28), (10, 14), (5, 7)], 4, "uniform"),       # boxes overflow -> global path
     "two_levels_p8": (1, 8, [(24, 40), (12, 20)], 8, "model"),
     "heads4": (1, 4, [(33, 47), (17, 24), (9, 12)], 4, "model"),
+    "smooth_c1": (2, 8, [(60, 80), (30, 40), (15, 20), (8, 10)], 4, "smooth"),
     "l8_p4": (1, 8, [(20, 30), (10, 15), (5, 8), (3, 4)] * 2, 4, "model"),
 }
 
@@ -392,12 +404,20 @@ def test_tiled_encoder_forward_equals_general_kernel(msda, dev, name):
             ys, xs = torch.meshgrid(torch.arange(h) + 0.5, torch.arange(w) + 0.5, indexing="ij")
             refs.append(torch.stack([xs.reshape(-1) / w, ys.reshape(-1) / h], -1))
         ref = torch.cat(refs, 0)[None, :, None, None, None, :]
-        off = torch.randn(N, S, M, L, P, 2, generator=g) * 2.5
+        if dist == "smooth":         # what a model produces: per-(head, level, point) offsets + a little jitter
+            off = torch.randn(1, 1, M, L, P, 2, generator=g) * 2.5 + 0.2 * torch.randn(N, S, M, L, P, 2, generator=g)
+        else:
+            off = torch.randn(N, S, M, L, P, 2, generator=g) * 2.5
         loc = ref + off / shapes.flip(-1).float()[None, None, None, :, None, :]
     attn = torch.softmax(torch.randn(N, S, M, L * P, generator=g), -1).view(N, S, M, L, P)
     tv, ts, tl, ta = value.to(dev), shapes.to(dev), loc.to(dev), attn.to(dev)
     flat_hw = [int(v) for pair in hw for v in pair]
-    tiled = msda.ms_deform_attn_forward_enc(tv, ts, tl, ta, flat_hw, 64)
+    if P == 4 and L <= 4:            # the tiled kernel's domain: make sure IT produced the numbers, not the fallback
+        tiled = msda.ms_deform_attn_forward_enc_strict(tv, ts, tl, ta, flat_hw, 64)
+    else:
+        with pytest.raises(RuntimeError):
+            msda.ms_deform_attn_forward_enc_strict(tv, ts, tl, ta, flat_hw, 64)
+        tiled = msda.ms_deform_attn_forward_enc(tv, ts, tl, ta, flat_hw, 64)
     general = msda.ms_deform_attn_forward(tv, ts, tl, ta, 64)
     torch.testing.assert_close(tiled, general, rtol=1e-5, atol=1e-5)     # different summation order, same taps
     ref_out = msda_oracle.msda_forward(value.numpy(), shapes.numpy(), loc.numpy(), attn.numpy())
@@ -431,8 +451,9 @@ def _encoder_problem(name, D=32):
     return value, shapes, loc, attn, gout
 
 
-# 0 = automatic choice, 100 / 101 = run kernels (R = 8 / 4), 110 = warp-per-group kernels, 20 = 8-lane-group kernels
-@pytest.mark.parametrize("variant", [0, 100, 101, 110, 20])
+# 0 = automatic choice, 100 / 101 = run kernels (R = 8 / 4), 120 / 121 = second-generation run kernels (4 / 2 slots
+# interleaved), 110 = warp-per-group kernels, 20 = 8-lane-group kernels
+@pytest.mark.parametrize("variant", [0, 100, 101, 110, 120, 121, 20])
 @pytest.mark.parametrize("name", sorted(TILE_CASES))
 def test_kernel_families_match_c_oracle(msda, dev, name, variant):
     """Forward and fused backward of every specialised kernel family on encoder-shaped problems (incl. the FULL
@@ -454,10 +475,10 @@ def test_kernel_families_match_c_oracle(msda, dev, name, variant):
     scale = max(1.0, float(np.abs(ref_gv).max()))
     np.testing.assert_allclose(gv.cpu().numpy(), ref_gv, rtol=F32["rtol"], atol=F32["atol"] * scale)
     np.testing.assert_allclose(ga.cpu().numpy(), ref_ga, **F32)
-    np.testing.assert_allclose(gl.cpu().numpy(), ref_gl, rtol=F32["rtol"] * 5, atol=F32["atol"] * 50)
+    assert_close_but_for_ties(gl.cpu().numpy(), ref_gl, rtol=F32["rtol"] * 5, atol=F32["atol"] * 50)
 
 
-@pytest.mark.parametrize("variant", [100, 101, 110])
+@pytest.mark.parametrize("variant", [100, 101, 110, 120, 121])
 def test_kernel_families_on_degenerate_and_ragged_shapes(msda, dev, variant):
     """levels with a single row / column (on-the-fly predicated path), Lq not a multiple of the run block, M = 4 and
     12 heads, L*P = 64 (the largest supported; > 48 KB of dynamic shared memory), out-of-range locations"""

@@ -141,12 +141,12 @@ def main():
         for kind, variants, nbytes in (("fwd", args.variants, fwd_b), ("bwd", args.bwd_variants, bwd_b)):
             for v in [int(x) for x in variants.split(",")]:
                 if kind == "fwd":
-                    msda.set_variant(0 if v == -1 else v, 0)
-                    if v == -1:      # tiled encoder kernel (needs Lq == S)
+                    msda.set_variant(0 if v == -1 else (201 if v == -2 else v), 0)
+                    if v in (-1, -2):      # TMA-staged tile kernel of the encoder (needs Lq == S); -2: four-warp variant
                         if dims["Lq"] != dims["S"]:
                             continue
                         flat_hw = [int(x) for x in shapes.cpu().flatten().tolist()]
-                        fn = lambda: msda.ms_deform_attn_forward_enc(value, shapes, loc, attn, flat_hw, 64)
+                        fn = lambda: msda.ms_deform_attn_forward_enc_strict(value, shapes, loc, attn, flat_hw, 64)
                     else:
                         fn = lambda: msda.ms_deform_attn_forward(value, shapes, loc, attn, 64)
                 else:

@@ -28,8 +28,9 @@
 #include "msda_common.cuh"
 #include "msda_d32.cuh"
 #include "msda_d36.cuh"
-#include "msda_run.cuh"
-#include "msda_tile.cuh"
+#include "msda_run2.cuh"
+#include "msda_enc_tma.cuh"
+#include "tma_host.h"
 
 namespace msda {
 
@@ -245,7 +246,7 @@ static cudaError_t ensure_dyn_smem(K kernel, size_t bytes, std::atomic<size_t>& 
 //   run  : large query sets (encoder) -- register-resident sliding windows over runs of consecutive queries
 //   wide : small query sets (decoder) -- one warp per (n, q, m) group
 //   d32  : everything in between (and M % 4 != 0): one 8-lane group per (n, q, m), tap tables in shared memory
-enum class Family { kD32, kRun8, kRun4, kWide };
+enum class Family { kD32, kRun8, kRun4, kRun2, kWide };
 static Family pick_family(int variant, int64_t groups, const struct Dims& d);
 
 #define MSDA_LAUNCH_FWD(VEC_, G_, IT_)                                                       \
@@ -276,10 +277,15 @@ static Family pick_family(int variant, int64_t groups, const Dims& d) {
   const bool run_ok = (d.M % kRunHeads == 0);
   if (variant == 100) return run_ok ? Family::kRun8 : Family::kD32;
   if (variant == 101) return run_ok ? Family::kRun4 : Family::kD32;
+  if (variant == 120 || variant == 121) return run_ok ? Family::kRun2 : Family::kD32;
   if (variant == 110) return Family::kWide;
   if (variant != 0) return Family::kD32;                    // the older tuning codes address the d32 kernels
   if (groups <= 32768) return Family::kWide;
-  if (run_ok && d.Lq >= 2048) return Family::kRun8;
+  // Measured on B200 (profiles/r2_opbench_v1.json, r2_opbench_v2.json): the run kernels cut the rows through L1 to
+  // ~0.3x but serialise one window load per group and need 41-49 KB of shared memory per CTA (little L1 left), and end
+  // up latency bound -- C2 encoder forward 121 us (run8) / 96 us (run4) / 106 us (run2) against 102 us for the
+  // 8-lane-group kernels, backward 286 / 228 vs 235 us.  They stay selectable (variants 100, 101, 120, 121).
+  (void)run_ok;
   return Family::kD32;
 }
 
@@ -301,8 +307,31 @@ static int forward_impl(const T* value, const int64_t* shapes, const T* loc, con
     if (variant != 1 && vec_ok && (d.D == 32 || d.D == 36) && LP <= kMaxLP && aligned16(loc) && aligned16(attn) &&
         groups < (int64_t(1) << 31)) {
       const Family fam = pick_family(variant, groups, d);
-      if (fam == Family::kRun8 || fam == Family::kRun4) {
-        const int R = fam == Family::kRun8 ? 8 : 4, LG = d.D / 4;
+      if (fam == Family::kRun2 && d.D == 32) {
+        // second-generation run kernels (msda_run2.cuh): planned windows, FFMA2, NS interleaved slots
+        const int NS = (variant == 121 || d.P % 4 != 0) ? 2 : 4;
+        constexpr int R = 8;
+        const int qblocks = (d.Lq + 4 * R - 1) / (4 * R);
+        const int64_t units = int64_t(d.N) * qblocks * (d.M / kRunHeads);
+        const size_t smem = fwd_run2_smem_bytes(R, LP);
+        if (units < (int64_t(1) << 31) && d.P % NS == 0 && smem <= 220 * 1024) {
+#define MSDA_FWD_RUN2(NS_, LPCT_)                                                                                   \
+  do {                                                                                                              \
+    MSDA_ENSURE_SMEM((msda_fwd_run2_kernel<R, NS_, LPCT_>), smem);                                                  \
+    msda_fwd_run2_kernel<R, NS_, LPCT_><<<unsigned(units), kRunThreads, smem, st>>>(value, shapes, loc, attn, out,   \
+                                                                                   d.S, d.M, d.L, d.Lq, d.P, qblocks); \
+  } while (0)
+          if (NS == 4 && LP == 16) MSDA_FWD_RUN2(4, 16);
+          else if (NS == 4) MSDA_FWD_RUN2(4, 0);
+          else if (LP == 16) MSDA_FWD_RUN2(2, 16);
+          else MSDA_FWD_RUN2(2, 0);
+#undef MSDA_FWD_RUN2
+          g_launches.fetch_add(1, std::memory_order_relaxed);
+          return int(cudaGetLastError());
+        }
+      }
+      if (fam == Family::kRun8 || fam == Family::kRun4 || fam == Family::kRun2) {
+        const int R = fam == Family::kRun4 ? 4 : 8, LG = d.D / 4;
         const int QB = run_runs(LG) * R;
         const int qblocks = (d.Lq + QB - 1) / QB;
         const int64_t units = int64_t(d.N) * qblocks * (d.M / kRunHeads);
@@ -440,8 +469,8 @@ static int backward_impl(const T* value, const int64_t* shapes, const T* loc, co
     if (variant != 1 && vec_ok && (d.D == 32 || d.D == 36) && LP <= kMaxLP && aligned16(loc) && aligned16(attn) &&
         aligned16(gloc) && aligned16(gattn) && groups < (int64_t(1) << 31)) {
       const Family fam = pick_family(variant, groups, d);
-      if (fam == Family::kRun8 || fam == Family::kRun4) {
-        const int R = fam == Family::kRun8 ? 8 : 4, LG = d.D / 4;
+      if (fam == Family::kRun8 || fam == Family::kRun4 || fam == Family::kRun2) {
+        const int R = fam == Family::kRun4 ? 4 : 8, LG = d.D / 4;
         const int QB = run_runs(LG) * R;
         const int qblocks = (d.Lq + QB - 1) / QB;
         const int64_t units = int64_t(d.N) * qblocks * (d.M / kRunHeads);
@@ -601,7 +630,7 @@ int msda_b200_l1_gather_probe(const float* table, float* sink, int64_t rows, int
   return int(cudaGetLastError());
 }
 
-int msda_b200_variant_allows_tiles(void) { return g_fwd_variant.load() == 0 ? 1 : 0; }
+int msda_b200_variant_allows_tiles(void) { const int v = g_fwd_variant.load(); return (v == 0 || v >= 200) ? 1 : 0; }
 
 int msda_b200_forward_f32(const float* value, const int64_t* spatial_shapes, const float* sampling_loc,
                           const float* attn_weight, float* output, int N, int S, int M, int D, int L,
@@ -697,41 +726,71 @@ int msda_b200_backward_fused_f32(const float* value, const int64_t* spatial_shap
   return int(cudaGetLastError());
 }
 
+// value of image n, level l, viewed as [N][H_l][W_l][M][32] floats; box = 32 channels x 1 head x bw x bh pixels
+static bool et_make_map(CUtensorMap* map, const float* level_base, int N, int S, int M, int H, int W, int bw, int bh) {
+  tfb200::EncodeTiledFn fn = tfb200::tensor_map_encoder();
+  if (!fn) return false;
+  const cuuint64_t dims[5] = {32, cuuint64_t(M), cuuint64_t(W), cuuint64_t(H), cuuint64_t(N)};
+  const cuuint64_t strides[4] = {128, cuuint64_t(M) * 128, cuuint64_t(W) * M * 128, cuuint64_t(S) * M * 128};
+  const cuuint32_t box[5] = {32, 1, cuuint32_t(bw), cuuint32_t(bh), 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(level_base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Fills the tile geometry and the tensor maps of the encoder tile kernels; MSDA_E_UNSUPPORTED outside their domain.
+static int et_prepare(const float* value, const int64_t* spatial_shapes_host, int N, int S, int M, int D, int L, int Lq,
+                      int P, EtGeom* g, EtMaps* maps, int64_t* grid) {
+  if (D != 32 || L > kEtMaxL || P != kEtP || Lq != S || N < 1 || M > 65535) return MSDA_E_UNSUPPORTED;
+  if (!aligned16(value)) return MSDA_E_UNSUPPORTED;
+  g->L = L; g->S = S; g->M = M; g->Lq = Lq;
+  int64_t acc = 0;
+  int tiles = 0;
+  for (int l = 0; l < kEtMaxL; ++l) {
+    g->H[l] = g->W[l] = 2; g->start[l] = 0; g->tiles_x[l] = 1; g->tile_begin[l + 1] = 0;
+  }
+  for (int l = 0; l < L; ++l) {
+    const int64_t h = spatial_shapes_host[2 * l], w = spatial_shapes_host[2 * l + 1];
+    if (h < 2 || w < 2 || h > 32767 || w > 32767) return MSDA_E_UNSUPPORTED;
+    g->H[l] = int(h); g->W[l] = int(w); g->start[l] = int(acc);
+    g->tiles_x[l] = int((w + kEtTX - 1) / kEtTX);
+    g->tile_begin[l] = tiles;
+    tiles += g->tiles_x[l] * int((h + kEtTY - 1) / kEtTY);
+    acc += h * w;
+  }
+  for (int l = L; l <= kEtMaxL; ++l) g->tile_begin[l] = tiles;
+  if (acc != S) return MSDA_E_UNSUPPORTED;
+  *grid = int64_t(tiles) * M * N;
+  if (*grid > INT32_MAX) return MSDA_E_UNSUPPORTED;
+  for (int lq = 0; lq < L; ++lq)
+    for (int l = lq; l < L; ++l)
+      if (!et_make_map(&maps->m[et_map_index(lq, l)], value + size_t(g->start[l]) * M * 32, N, S, M, g->H[l], g->W[l],
+                       et_bw(l - lq), et_bh(l - lq)))
+        return MSDA_E_UNSUPPORTED;
+  return 0;
+}
+
 int msda_b200_forward_enc_tiled_f32(const float* value, const int64_t* spatial_shapes_host, const float* sampling_loc,
                                     const float* attn_weight, float* output, int N, int S, int M, int D, int L,
                                     int Lq, int P, void* stream) {
   const Dims d{N, S, M, D, L, Lq, P};
   if (int rc = check_dims(d)) return rc;
   if (!value || !spatial_shapes_host || !sampling_loc || !attn_weight || !output) return MSDA_E_NULLPTR;
-  if (D != 32 || L > kTileMaxLevels || L * P > kMaxLP || Lq != S || N < 1) return MSDA_E_UNSUPPORTED;
-  if (!aligned16(value) || !aligned16(sampling_loc) || !aligned16(attn_weight) || !aligned16(output))
-    return MSDA_E_UNSUPPORTED;
-  TileGeom g;
-  g.L = L; g.P = P; g.S = S; g.M = M;
-  int64_t acc = 0;
-  int tiles = 0;
-  for (int l = 0; l < L; ++l) {
-    const int64_t h = spatial_shapes_host[2 * l], w = spatial_shapes_host[2 * l + 1];
-    if (h < 2 || w < 2 || h > 65535 || w > 65535) return MSDA_E_UNSUPPORTED;
-    g.H[l] = int(h); g.W[l] = int(w); g.start[l] = int(acc);
-    g.tiles_x[l] = int((w + kTileX - 1) / kTileX);
-    g.tile_begin[l] = tiles;
-    tiles += g.tiles_x[l] * int((h + kTileY - 1) / kTileY);
-    acc += h * w;
+  if (!aligned16(sampling_loc) || !aligned16(attn_weight) || !aligned16(output)) return MSDA_E_UNSUPPORTED;
+  EtGeom g;
+  EtMaps maps;
+  int64_t grid = 0;
+  if (int rc = et_prepare(value, spatial_shapes_host, N, S, M, D, L, Lq, P, &g, &maps, &grid)) return rc;
+  if (g_fwd_variant.load(std::memory_order_relaxed) == 201) {        // A/B: four warps, four slots per warp
+    MSDA_ENSURE_SMEM(msda_fwd_enc_tma_kernel<4>, kEtSmemBytes);
+    msda_fwd_enc_tma_kernel<4><<<unsigned(grid), 128, kEtSmemBytes, cudaStream_t(stream)>>>(value, sampling_loc, attn_weight,
+                                                                                           output, g, maps);
+  } else {
+    MSDA_ENSURE_SMEM(msda_fwd_enc_tma_kernel<2>, kEtSmemBytes);
+    msda_fwd_enc_tma_kernel<2><<<unsigned(grid), kEtThreads, kEtSmemBytes, cudaStream_t(stream)>>>(value, sampling_loc,
+                                                                                                  attn_weight, output, g, maps);
   }
-  g.tile_begin[L] = tiles;
-  if (acc != S) return MSDA_E_UNSUPPORTED;
-  const int64_t grid = int64_t(tiles) * M * N;
-  if (grid > INT32_MAX) return MSDA_E_UNSUPPORTED;
-  const size_t smem = fwd_tile_smem_bytes(L * P);
-  static std::atomic<bool> attr_set{false};
-  if (!attr_set.load()) {
-    cudaError_t e = cudaFuncSetAttribute(msda_fwd_enc_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e != cudaSuccess) return int(e);
-    attr_set.store(true);
-  }
-  msda_fwd_enc_tile_kernel<<<unsigned(grid), kD32Threads, smem, cudaStream_t(stream)>>>(value, sampling_loc, attn_weight,
-                                                                                        output, g);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return int(cudaGetLastError());
 }

@@ -168,9 +168,26 @@ std::vector<at::Tensor> ms_deform_attn_backward_fused(const at::Tensor& value, c
   return {gv, gp};
 }
 
+static at::Tensor forward_enc_impl(const at::Tensor& value, const at::Tensor& spatial_shapes,
+                                   const at::Tensor& sampling_loc, const at::Tensor& attn_weight,
+                                   const std::vector<int64_t>& hw, const int64_t im2col_step, bool strict);
+
 at::Tensor ms_deform_attn_forward_enc(const at::Tensor& value, const at::Tensor& spatial_shapes,
                                       const at::Tensor& sampling_loc, const at::Tensor& attn_weight,
                                       const std::vector<int64_t>& hw, const int64_t im2col_step) {
+  return forward_enc_impl(value, spatial_shapes, sampling_loc, attn_weight, hw, im2col_step, false);
+}
+
+// the same, but raises instead of falling back to the general kernel (tests: proves which kernel produced the numbers)
+at::Tensor ms_deform_attn_forward_enc_strict(const at::Tensor& value, const at::Tensor& spatial_shapes,
+                                             const at::Tensor& sampling_loc, const at::Tensor& attn_weight,
+                                             const std::vector<int64_t>& hw, const int64_t im2col_step) {
+  return forward_enc_impl(value, spatial_shapes, sampling_loc, attn_weight, hw, im2col_step, true);
+}
+
+static at::Tensor forward_enc_impl(const at::Tensor& value, const at::Tensor& spatial_shapes,
+                                   const at::Tensor& sampling_loc, const at::Tensor& attn_weight,
+                                   const std::vector<int64_t>& hw, const int64_t im2col_step, bool strict) {
   const Geometry g = validate(value, spatial_shapes, sampling_loc, attn_weight, im2col_step);
   if (value.scalar_type() == at::kFloat && int64_t(hw.size()) == 2 * int64_t(g.L) && msda_b200_variant_allows_tiles()) {
     const c10::cuda::CUDAGuard guard(value.device());
@@ -183,6 +200,7 @@ at::Tensor ms_deform_attn_forward_enc(const at::Tensor& value, const at::Tensor&
     if (rc == 0) return out;
     if (rc != MSDA_E_UNSUPPORTED) raise_on_error(rc, "ms_deform_attn_forward_enc");
   }
+  TORCH_CHECK(!strict, "ms_deform_attn_forward_enc: outside the tiled kernel's domain (fp32, D = 32, P = 4, L <= 4, Lq == S)");
   return ms_deform_attn_forward(value, spatial_shapes, sampling_loc, attn_weight, im2col_step);
 }
 
@@ -618,6 +636,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("launch_count", []() { return msda_b200_launch_count(); });
   m.def("set_variant", [](int f, int b) { msda_b200_set_variant(f, b); });
   m.def("ms_deform_attn_forward_enc", &ms_deform_attn_forward_enc);
+  m.def("ms_deform_attn_forward_enc_strict", &ms_deform_attn_forward_enc_strict);
   m.def("ms_deform_attn_forward_fused", &ms_deform_attn_forward_fused);
   m.def("ms_deform_attn_backward_fused", &ms_deform_attn_backward_fused);
   m.def("add_dropout_layernorm_forward", &add_dropout_layernorm_forward);

@@ -32,10 +32,10 @@
 #include <stdint.h>
 
 #include <atomic>
-#include <mutex>
 
 #include "../../include/tfb200_fused.h"
 #include "launch_counter.h"
+#include "tma_host.h"
 
 namespace tfb200 {
 namespace gemm {
@@ -99,15 +99,19 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
   return d;
 }
 
-// MN-major operand tile (the contraction index is the strided one), SWIZZLE_128B: 32-feature (128-byte) blocks of
-// 32 contraction rows each; blocks are MN_BLOCK_BYTES apart (leading byte offset), 8-row groups 1024 bytes apart
+// MN-major operand tile (the contraction index is the strided one).  For 32-bit element types the tensor core accepts
+// exactly one swizzled MN-major layout: "128-byte swizzle with 32-byte atomicity" (UMMA layout type 1, the byte-address
+// swizzle XORs bits [5,7) with bits [7,9); the TMA unit writes it with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  Canonical
+// form, in 16-byte units: ((8, n), (4, k)) : ((1, LBO), (8, SBO)) -- a 128-byte row holds 32 consecutive features of one
+// contraction row, 4 rows make a 512-byte swizzle atom, the next 4 contraction rows are SBO away and the next 32-feature
+// block LBO away.  A tile is staged as 32-feature x 32-row TMA boxes (4 KB each, dense 128-byte rows).
 constexpr int MN_BLOCK_BYTES = BK * 128;                 // 32 rows x 128 bytes = 4 KB
 __device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr) {
   uint64_t d = uint64_t((saddr & 0x3FFFFu) >> 4);
   d |= uint64_t(MN_BLOCK_BYTES >> 4) << 16;              // leading byte offset: next 32-feature block
-  d |= uint64_t(1024 >> 4) << 32;                        // stride byte offset: next 8 contraction rows
+  d |= uint64_t(512 >> 4) << 32;                         // stride byte offset: next 4 contraction rows
   d |= uint64_t(1) << 46;
-  d |= uint64_t(2) << 61;
+  d |= uint64_t(1) << 61;                                // layout: SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -321,33 +325,19 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-// row-major [rows, cols] fp32 matrix, box = 32 columns x `box_rows` rows, 128-byte swizzle
-static bool make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int box_rows = 128) {
-  EncodeTiledFn fn = encode_fn();
+// row-major [rows, cols] fp32 matrix, box = 32 columns x `box_rows` rows; 128-byte swizzle, with 32-byte atomicity for
+// the boxes of an MN-major operand (see smem_desc_mn)
+static bool make_map(CUtensorMap* map, const float* ptr, int64_t rows, int64_t cols, int box_rows = 128,
+                     bool mn_major = false) {
+  tfb200::EncodeTiledFn fn = tfb200::tensor_map_encoder();
   if (!fn) return false;
   const cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
   const cuuint64_t strides[1] = {cuuint64_t(cols) * 4};
   const cuuint32_t box[2] = {32, cuuint32_t(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -397,9 +387,10 @@ extern "C" int tfb200_tf32_linear_supported(int64_t M, int N, int K) {
 extern "C" int tfb200_tf32_linear_f32(const float* x, const float* w, const float* bias, float* y, int64_t M, int N,
                                       int K, int relu, void* stream) {
   if (!x || !w || !y) return -1;
-  if (M < 1 || N % BN || K % BK || N < BN || K < BK || misaligned(x, w, y, bias)) return -5;
+  if (M < 1 || N % BN || K % BK || N < BN || K < BK) return -5;
+  if (misaligned(x, w, y, bias)) return -6;
   CUtensorMap mx, mw, my;
-  if (!make_map(&mx, x, M, K) || !make_map(&mw, w, N, K) || !make_map(&my, y, M, N)) return -5;
+  if (!make_map(&mx, x, M, K) || !make_map(&mw, w, N, K) || !make_map(&my, y, M, N)) return -7;
   const int m_tiles = int((M + BM - 1) / BM), n_tiles = N / BN, k_blocks = K / BK;
   return relu ? launch<kModeLinear, true>(mx, mw, my, bias, m_tiles, n_tiles, k_blocks, 1, cudaStream_t(stream))
               : launch<kModeLinear, false>(mx, mw, my, bias, m_tiles, n_tiles, k_blocks, 1, cudaStream_t(stream));
@@ -408,22 +399,24 @@ extern "C" int tfb200_tf32_linear_f32(const float* x, const float* w, const floa
 extern "C" int tfb200_tf32_linear_dgrad_f32(const float* dy, const float* w, float* dx, int64_t M, int N, int K,
                                             void* stream) {
   if (!dy || !w || !dx) return -1;
-  if (M < 1 || N % BK || K % BN || N < BK || K < BN || misaligned(dy, w, dx)) return -5;
+  if (M < 1 || N % BK || K % BN || N < BK || K < BN) return -5;
+  if (misaligned(dy, w, dx)) return -6;
   CUtensorMap ma, mb, mo;
   // A = dy [M, N] K-major; B = w [N, K] read as 32-feature x 32-row boxes; output dx [M, K]
-  if (!make_map(&ma, dy, M, N) || !make_map(&mb, w, N, K, 32) || !make_map(&mo, dx, M, K)) return -5;
+  if (!make_map(&ma, dy, M, N) || !make_map(&mb, w, N, K, 32, true) || !make_map(&mo, dx, M, K)) return -7;
   return launch<kModeDgrad, false>(ma, mb, mo, nullptr, int((M + BM - 1) / BM), K / BN, N / BK, 1, cudaStream_t(stream));
 }
 
 extern "C" int tfb200_tf32_linear_wgrad_f32(const float* dy, const float* x, float* dw, int64_t M, int N, int K,
                                             void* stream) {
   if (!dy || !x || !dw) return -1;
-  if (M < 1 || N % BM || K % BN || N < BM || K < BN || misaligned(dy, x, dw)) return -5;
+  if (M < 1 || N % BM || K % BN || N < BM || K < BN) return -5;
+  if (misaligned(dy, x, dw)) return -6;
   cudaStream_t st = cudaStream_t(stream);
   cudaError_t e = cudaMemsetAsync(dw, 0, size_t(N) * K * 4, st);       // the slabs are ADDED into dw
   if (e != cudaSuccess) return int(e);
   CUtensorMap ma, mb, mo;
-  if (!make_map(&ma, dy, M, N, 32) || !make_map(&mb, x, M, K, 32) || !make_map(&mo, dw, N, K)) return -5;
+  if (!make_map(&ma, dy, M, N, 32, true) || !make_map(&mb, x, M, K, 32, true) || !make_map(&mo, dw, N, K)) return -7;
   const int m_tiles = N / BM, n_tiles = K / BN, k_blocks = int((M + BK - 1) / BK);
   int splits = sm_count() / (m_tiles * n_tiles);
   if (splits < 1) splits = 1;
