@@ -104,6 +104,13 @@ int msda_b200_backward_fused_f32(const float* value, const int64_t* spatial_shap
 int msda_b200_forward_enc_tiled_f32(const float* value, const int64_t* spatial_shapes_host,
                                     const float* sampling_loc, const float* attn_weight, float* output,
                                     int N, int S, int M, int D, int L, int Lq, int P, void* stream);
+/* Backward twin (same contract as msda_b200_backward_f32: grad_value is zero-filled and accumulated, the other two are
+ * overwritten; replaces ms_deform_attn_cuda_backward, ms_deform_attn_cuda.cu:89-168, for encoder call sites).  Domain as
+ * the forward, plus H, W <= 4095 and S < 2^20.                                                                   */
+int msda_b200_backward_enc_tiled_f32(const float* value, const int64_t* spatial_shapes_host,
+                                     const float* sampling_loc, const float* attn_weight, const float* grad_output,
+                                     float* grad_value, float* grad_sampling_loc, float* grad_attn_weight,
+                                     int N, int S, int M, int D, int L, int Lq, int P, void* stream);
 
 /* ---- host-buffer entry points (H2D + kernel + D2H inside the call; synchronous) -------- */
 int msda_b200_forward_host_f32(const float* value, const int64_t* spatial_shapes,

@@ -424,6 +424,29 @@ def test_tiled_encoder_forward_equals_general_kernel(msda, dev, name):
     np.testing.assert_allclose(tiled.cpu().numpy(), ref_out, **F32)
 
 
+@pytest.mark.parametrize("name", sorted(TILE_CASES))
+def test_tiled_encoder_backward_matches_c_oracle(msda, dev, name):
+    """The TMA-staged backward tile kernel (strict: no fallback inside its domain) against the C restatement of the
+    reference's backward kernels, on the same encoder-shaped problems as the kernel families below."""
+    from oracle import msda_oracle
+    N, M, hw, P, dist = TILE_CASES[name]
+    value, shapes, loc, attn, gout = _encoder_problem(name)
+    ref_gv, ref_gl, ref_ga = msda_oracle.msda_backward(value.numpy(), shapes.numpy(), loc.numpy(), attn.numpy(), gout.numpy())
+    tv, ts, tl, ta, tg = (x.to(dev) for x in (value, shapes, loc, attn, gout))
+    flat_hw = [int(v) for pair in hw for v in pair]
+    if P == 4 and len(hw) <= 4:
+        gv, gl, ga = msda.ms_deform_attn_backward_enc_strict(tv, ts, tl, ta, tg, flat_hw, 64)
+    else:
+        with pytest.raises(RuntimeError):
+            msda.ms_deform_attn_backward_enc_strict(tv, ts, tl, ta, tg, flat_hw, 64)
+        gv, gl, ga = msda.ms_deform_attn_backward_enc(tv, ts, tl, ta, tg, flat_hw, 64)
+    torch.cuda.synchronize()
+    scale = max(1.0, float(np.abs(ref_gv).max()))
+    np.testing.assert_allclose(gv.cpu().numpy(), ref_gv, rtol=F32["rtol"], atol=F32["atol"] * scale)
+    np.testing.assert_allclose(ga.cpu().numpy(), ref_ga, **F32)
+    assert_close_but_for_ties(gl.cpu().numpy(), ref_gl, rtol=F32["rtol"] * 5, atol=F32["atol"] * 50)
+
+
 # ----------------------------------------------------------------------------- every fp32 / D = 32 kernel family
 def _encoder_problem(name, D=32):
     N, M, hw, P, dist = TILE_CASES[name]

@@ -150,8 +150,14 @@ def main():
                     else:
                         fn = lambda: msda.ms_deform_attn_forward(value, shapes, loc, attn, 64)
                 else:
-                    msda.set_variant(0, v)
-                    fn = lambda: msda.ms_deform_attn_backward(value, shapes, loc, attn, gout, 64)
+                    msda.set_variant(0, 0 if v == -1 else v)
+                    if v == -1:      # TMA-staged backward tile kernel of the encoder
+                        if dims["Lq"] != dims["S"]:
+                            continue
+                        flat_hw = [int(x) for x in shapes.cpu().flatten().tolist()]
+                        fn = lambda: msda.ms_deform_attn_backward_enc_strict(value, shapes, loc, attn, gout, flat_hw, 64)
+                    else:
+                        fn = lambda: msda.ms_deform_attn_backward(value, shapes, loc, attn, gout, 64)
                 fn()
                 torch.cuda.synchronize()
                 if args.once:

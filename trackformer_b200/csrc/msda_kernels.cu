@@ -29,7 +29,7 @@
 #include "msda_d32.cuh"
 #include "msda_d36.cuh"
 #include "msda_run2.cuh"
-#include "msda_enc_tma.cuh"
+#include "msda_enc_tma_bwd.cuh"
 #include "tma_host.h"
 
 namespace msda {
@@ -741,8 +741,9 @@ static bool et_make_map(CUtensorMap* map, const float* level_base, int N, int S,
 
 // Fills the tile geometry and the tensor maps of the encoder tile kernels; MSDA_E_UNSUPPORTED outside their domain.
 static int et_prepare(const float* value, const int64_t* spatial_shapes_host, int N, int S, int M, int D, int L, int Lq,
-                      int P, EtGeom* g, EtMaps* maps, int64_t* grid) {
+                      int P, EtGeom* g, EtMaps* maps, int64_t* grid, bool backward) {
   if (D != 32 || L > kEtMaxL || P != kEtP || Lq != S || N < 1 || M > 65535) return MSDA_E_UNSUPPORTED;
+  if (backward && S >= (1 << 20)) return MSDA_E_UNSUPPORTED;          // 20-bit pixel indices in the backward's tap words
   if (!aligned16(value)) return MSDA_E_UNSUPPORTED;
   g->L = L; g->S = S; g->M = M; g->Lq = Lq;
   int64_t acc = 0;
@@ -753,6 +754,7 @@ static int et_prepare(const float* value, const int64_t* spatial_shapes_host, in
   for (int l = 0; l < L; ++l) {
     const int64_t h = spatial_shapes_host[2 * l], w = spatial_shapes_host[2 * l + 1];
     if (h < 2 || w < 2 || h > 32767 || w > 32767) return MSDA_E_UNSUPPORTED;
+    if (backward && (h > 4095 || w > 4095)) return MSDA_E_UNSUPPORTED;  // 12-bit window corners in the backward's tap words
     g->H[l] = int(h); g->W[l] = int(w); g->start[l] = int(acc);
     g->tiles_x[l] = int((w + kEtTX - 1) / kEtTX);
     g->tile_begin[l] = tiles;
@@ -766,7 +768,7 @@ static int et_prepare(const float* value, const int64_t* spatial_shapes_host, in
   for (int lq = 0; lq < L; ++lq)
     for (int l = lq; l < L; ++l)
       if (!et_make_map(&maps->m[et_map_index(lq, l)], value + size_t(g->start[l]) * M * 32, N, S, M, g->H[l], g->W[l],
-                       et_bw(l - lq), et_bh(l - lq)))
+                       backward ? eb_bw(l - lq) : et_bw(l - lq), backward ? eb_bh(l - lq) : et_bh(l - lq)))
         return MSDA_E_UNSUPPORTED;
   return 0;
 }
@@ -781,7 +783,7 @@ int msda_b200_forward_enc_tiled_f32(const float* value, const int64_t* spatial_s
   EtGeom g;
   EtMaps maps;
   int64_t grid = 0;
-  if (int rc = et_prepare(value, spatial_shapes_host, N, S, M, D, L, Lq, P, &g, &maps, &grid)) return rc;
+  if (int rc = et_prepare(value, spatial_shapes_host, N, S, M, D, L, Lq, P, &g, &maps, &grid, false)) return rc;
   if (g_fwd_variant.load(std::memory_order_relaxed) == 201) {        // A/B: four warps, four slots per warp
     MSDA_ENSURE_SMEM(msda_fwd_enc_tma_kernel<4>, kEtSmemBytes);
     msda_fwd_enc_tma_kernel<4><<<unsigned(grid), 128, kEtSmemBytes, cudaStream_t(stream)>>>(value, sampling_loc, attn_weight,
@@ -791,6 +793,33 @@ int msda_b200_forward_enc_tiled_f32(const float* value, const int64_t* spatial_s
     msda_fwd_enc_tma_kernel<2><<<unsigned(grid), kEtThreads, kEtSmemBytes, cudaStream_t(stream)>>>(value, sampling_loc,
                                                                                                   attn_weight, output, g, maps);
   }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+
+int msda_b200_backward_enc_tiled_f32(const float* value, const int64_t* spatial_shapes_host, const float* sampling_loc,
+                                     const float* attn_weight, const float* grad_output, float* grad_value,
+                                     float* grad_sampling_loc, float* grad_attn_weight, int N, int S, int M, int D, int L,
+                                     int Lq, int P, void* stream) {
+  const Dims d{N, S, M, D, L, Lq, P};
+  if (int rc = check_dims(d)) return rc;
+  if (!value || !spatial_shapes_host || !sampling_loc || !attn_weight || !grad_output || !grad_value || !grad_sampling_loc ||
+      !grad_attn_weight)
+    return MSDA_E_NULLPTR;
+  if (!aligned16(sampling_loc) || !aligned16(attn_weight) || !aligned16(grad_output) || !aligned16(grad_value) ||
+      !aligned16(grad_sampling_loc) || !aligned16(grad_attn_weight))
+    return MSDA_E_UNSUPPORTED;
+  EtGeom g;
+  EtMaps maps;
+  int64_t grid = 0;
+  if (int rc = et_prepare(value, spatial_shapes_host, N, S, M, D, L, Lq, P, &g, &maps, &grid, true)) return rc;
+  cudaStream_t st = cudaStream_t(stream);
+  cudaError_t e = cudaMemsetAsync(grad_value, 0, sizeof(float) * size_t(N) * S * M * D, st);
+  if (e != cudaSuccess) return int(e);
+  MSDA_ENSURE_SMEM(msda_bwd_enc_tma_kernel, kEbSmemBytes);
+  msda_bwd_enc_tma_kernel<<<unsigned(grid), kEbThreads, kEbSmemBytes, st>>>(value, sampling_loc, attn_weight, grad_output,
+                                                                           grad_value, grad_sampling_loc, grad_attn_weight, g,
+                                                                           maps);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return int(cudaGetLastError());
 }

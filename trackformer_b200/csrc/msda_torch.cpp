@@ -131,8 +131,42 @@ std::vector<at::Tensor> ms_deform_attn_backward(const at::Tensor& value, const a
   return {grad_value, grad_loc, grad_attn};
 }
 
-// Encoder self-attention (queries == pixels): tiled kernel when the geometry allows, the general kernel otherwise.
-// `hw` is the host copy of spatial_shapes ([H0, W0, H1, W1, ...]) the caller already has.
+// Backward of the encoder self-attention: tiled kernel when the geometry allows, the general kernel otherwise
+// (strict: raise instead).  `hw` is the host copy of spatial_shapes ([H0, W0, H1, W1, ...]).
+static std::vector<at::Tensor> backward_enc_impl(const at::Tensor& value, const at::Tensor& spatial_shapes,
+                                                 const at::Tensor& sampling_loc, const at::Tensor& attn_weight,
+                                                 const at::Tensor& grad_output, const std::vector<int64_t>& hw,
+                                                 const int64_t im2col_step, bool strict) {
+  const Geometry g = validate(value, spatial_shapes, sampling_loc, attn_weight, im2col_step);
+  TORCH_CHECK(grad_output.is_cuda() && grad_output.scalar_type() == value.scalar_type() &&
+              grad_output.numel() == int64_t(g.N) * g.Lq * g.M * g.D, "grad_output must be a CUDA tensor [N, Lq, M*D]");
+  if (value.scalar_type() == at::kFloat && int64_t(hw.size()) == 2 * int64_t(g.L) && msda_b200_variant_allows_tiles()) {
+    const c10::cuda::CUDAGuard guard(value.device());
+    const at::Tensor loc = sampling_loc.contiguous(), attn = attn_weight.contiguous(), gout = grad_output.contiguous();
+    at::Tensor grad_value = at::empty_like(value), grad_loc = at::empty_like(loc), grad_attn = at::empty_like(attn);
+    const int rc = msda_b200_backward_enc_tiled_f32(
+        value.data_ptr<float>(), hw.data(), loc.data_ptr<float>(), attn.data_ptr<float>(), gout.data_ptr<float>(),
+        grad_value.data_ptr<float>(), grad_loc.data_ptr<float>(), grad_attn.data_ptr<float>(), g.N, g.S, g.M, g.D, g.L, g.Lq,
+        g.P, c10::cuda::getCurrentCUDAStream().stream());
+    if (rc == 0) return {grad_value, grad_loc, grad_attn};
+    if (rc != MSDA_E_UNSUPPORTED) raise_on_error(rc, "ms_deform_attn_backward_enc");
+  }
+  TORCH_CHECK(!strict, "ms_deform_attn_backward_enc: outside the tiled kernel's domain (fp32, D = 32, P = 4, L <= 4, Lq == S)");
+  return ms_deform_attn_backward(value, spatial_shapes, sampling_loc, attn_weight, grad_output, im2col_step);
+}
+std::vector<at::Tensor> ms_deform_attn_backward_enc(const at::Tensor& value, const at::Tensor& spatial_shapes,
+                                                    const at::Tensor& sampling_loc, const at::Tensor& attn_weight,
+                                                    const at::Tensor& grad_output, const std::vector<int64_t>& hw,
+                                                    const int64_t im2col_step) {
+  return backward_enc_impl(value, spatial_shapes, sampling_loc, attn_weight, grad_output, hw, im2col_step, false);
+}
+std::vector<at::Tensor> ms_deform_attn_backward_enc_strict(const at::Tensor& value, const at::Tensor& spatial_shapes,
+                                                           const at::Tensor& sampling_loc, const at::Tensor& attn_weight,
+                                                           const at::Tensor& grad_output, const std::vector<int64_t>& hw,
+                                                           const int64_t im2col_step) {
+  return backward_enc_impl(value, spatial_shapes, sampling_loc, attn_weight, grad_output, hw, im2col_step, true);
+}
+
 // fused-prologue variant: proj [N, Lq, 3*M*L*P] (raw [offsets | logits]), ref [N, Lq, L, 2]
 at::Tensor ms_deform_attn_forward_fused(const at::Tensor& value, const at::Tensor& spatial_shapes, const at::Tensor& proj,
                                         const at::Tensor& ref, int64_t n_points) {
@@ -637,6 +671,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_variant", [](int f, int b) { msda_b200_set_variant(f, b); });
   m.def("ms_deform_attn_forward_enc", &ms_deform_attn_forward_enc);
   m.def("ms_deform_attn_forward_enc_strict", &ms_deform_attn_forward_enc_strict);
+  m.def("ms_deform_attn_backward_enc", &ms_deform_attn_backward_enc);
+  m.def("ms_deform_attn_backward_enc_strict", &ms_deform_attn_backward_enc_strict);
   m.def("ms_deform_attn_forward_fused", &ms_deform_attn_forward_fused);
   m.def("ms_deform_attn_backward_fused", &ms_deform_attn_backward_fused);
   m.def("add_dropout_layernorm_forward", &add_dropout_layernorm_forward);

@@ -16,6 +16,8 @@ from __future__ import annotations
 
 import copy
 
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -39,6 +41,10 @@ def _activation(name: str):
 
 def _add_pos(x, pos):
     return x if pos is None else x + pos
+
+
+# A/B switch (measurement only): True forces nn.MultiheadAttention's unfused bmm / softmax / bmm path
+_MHA_NEED_WEIGHTS = os.environ.get("TFB200_MHA_NEED_WEIGHTS", "0") == "1"
 
 
 class DeformableTransformerEncoderLayer(nn.Module):
@@ -142,7 +148,8 @@ class DeformableTransformerDecoderLayer(nn.Module):
         # need_weights=False: the averaged attention map is never used (the reference discards it too,
         # deformable_transformer.py:368) and asking for it forces the unfused bmm / softmax / bmm path with ~25 small
         # launches per layer and direction; without it the module runs one fused attention kernel
-        sa = self.self_attn(qk, qk, tgt.transpose(0, 1), key_padding_mask=key_mask, need_weights=False)[0].transpose(0, 1)
+        sa = self.self_attn(qk, qk, tgt.transpose(0, 1), key_padding_mask=key_mask,
+                            need_weights=_MHA_NEED_WEIGHTS)[0].transpose(0, 1)
         tgt = add_dropout_layernorm(tgt, sa, self.dropout2, self.norm2)
         # deformable cross-attention into the encoder memory
         ca = self.cross_attn(_add_pos(tgt, query_pos), reference_points, src, src_spatial_shapes,

@@ -55,11 +55,16 @@ def weight_grad(gy2: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
 # Forward products of the long-token Linears on the hand-written tcgen05 kernel (csrc/tf32_gemm.cu) whenever TF32
 # tensor-core math is allowed (torch.backends.cuda.matmul.allow_tf32 -- the benchmark setting; strict-fp32 runs keep the
 # library's fp32 GEMM).  TFB200_TCGEN05_LINEAR=0 switches it off (A/B timing).
-_TCGEN05 = os.environ.get("TFB200_TCGEN05_LINEAR", "0") != "0"      # off until validated on a B200
+_TCGEN05 = os.environ.get("TFB200_TCGEN05_LINEAR", "1") != "0"
 
 
-# Which of the three products run on it: "fdw" = forward, dgrad, wgrad (default all three).
-_TCGEN05_PARTS = os.environ.get("TFB200_TCGEN05_PARTS", "fdw")
+# Which of the three products run on it ("f" forward, "d" dgrad, "w" wgrad).  Measured on B200 (tools/gemm_bench.py,
+# profiles/r2_gemm_bench.json; one-call A/B of the whole step, profiles/r2_ab_call10.txt): the split-token wgrad beats
+# the library 1.3-2x (23.5 vs 44 us for 256 x 256 x 22223, 27.6 vs 56 us for 384 x 256) -- the library runs that
+# product on 8-32 CTAs; forward and dgrad are on par for N = 256 / 384 and ~1.3x slower for the 1024-wide FFN products
+# (128 x 128 tiles leave a 2.35-wave tail and re-stage W per tile).  Step: 67.5 -> 70.8 frames/s with "w", 69.8 with
+# "dw", 69.2 with "fdw".  Default: the product where the hand-written kernel wins.
+_TCGEN05_PARTS = os.environ.get("TFB200_TCGEN05_PARTS", "w")
 
 
 def _tcgen05_ok(x, weight):

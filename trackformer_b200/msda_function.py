@@ -53,44 +53,100 @@ class MSDeformAttnFunction(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        value, shapes, loc, attn = ctx.saved_tensors
-        sink = _TIMING_SINK
-        if sink is not None:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+        return _backward(ctx, grad_output, None)
+
+
+def _backward(ctx, grad_output, hw):
+    """Fused backward launch (grad_value, grad_sampling_loc, grad_attn_weight); ``hw`` (host level sizes) selects the
+    encoder tile kernel."""
+    value, shapes, loc, attn = ctx.saved_tensors
+    sink = _TIMING_SINK
+    if sink is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    if hw is None:
         g_value, g_loc, g_attn = ext.load().ms_deform_attn_backward(
             value, shapes, loc, attn, grad_output.contiguous(), ctx.im2col_step)
-        if sink is not None:
-            e1.record()
-            sink.append(("bwd", _dims(value, loc), e0, e1))
-        return g_value, None, g_loc, g_attn, None
+    else:
+        g_value, g_loc, g_attn = ext.load().ms_deform_attn_backward_enc(
+            value, shapes, loc, attn, grad_output.contiguous(), hw, ctx.im2col_step)
+    if sink is not None:
+        e1.record()
+        sink.append(("bwd", _dims(value, loc), e0, e1))
+    return g_value, None, g_loc, g_attn, None
+
+
+# Which forward kernel serves an encoder call (queries == pixels): "tile" = the TMA-staged tile kernel
+# (csrc/msda_enc_tma.cuh), "direct" = the 8-lane-group kernel.  Which one is faster depends on how compact the sampling
+# pattern of neighbouring queries is (measured on B200, C2 encoder call: the grid pattern of a freshly initialised model
+# 82 vs 103 us, +-0.5 px of per-sample jitter 116 vs 106 us, uniformly random locations 224 vs 107 us), so in "auto"
+# mode the first eager call of a geometry times both on the data at hand and the winner is kept for that geometry.
+import os as _os
+
+_TILED_ENC = _os.environ.get("TFB200_TILED_ENC", "auto")            # "auto" | "1" (always tile) | "0" (never)
+_TILED_ENC_BWD = _os.environ.get("TFB200_TILED_ENC_BWD", "0") == "1"  # opt-in: correct, not yet faster (DESIGN.md 3)
+_ENC_CHOICE = {}
+
+
+def _time_us(fn, iters=3):
+    fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / iters
+
+
+def encoder_kernel_choice(msda, value, shapes, loc, attn, hw, step):
+    if _TILED_ENC in ("0", "1"):
+        return "tile" if _TILED_ENC == "1" else "direct"
+    key = (tuple(value.shape), tuple(hw), value.device.index)
+    choice = _ENC_CHOICE.get(key)
+    if choice is None:
+        if torch.cuda.is_current_stream_capturing():
+            return "direct"                                          # no timing inside a capture; decided by an eager call
+        t_tile = _time_us(lambda: msda.ms_deform_attn_forward_enc(value, shapes, loc, attn, hw, step))
+        t_direct = _time_us(lambda: msda.ms_deform_attn_forward(value, shapes, loc, attn, step))
+        choice = _ENC_CHOICE[key] = "tile" if t_tile < 0.97 * t_direct else "direct"
+    return choice
 
 
 class MSDeformAttnEncFunction(Function):
-    """Encoder self-attention variant (queries are the pixels, ``Lq == S``): the forward may run the
-    shared-memory tiled kernel, which needs the level sizes on the host -- taken from the ``_hw_list`` the
-    transformer attaches to ``value_spatial_shapes``.  Results and the backward are those of
-    :class:`MSDeformAttnFunction`; geometries the tiled kernel does not cover fall through to the general
-    kernel inside the extension (still CUDA -- there is no CPU path)."""
+    """Encoder self-attention variant (queries are the pixels, ``Lq == S``): the forward may run the TMA-staged tile
+    kernel, which needs the level sizes on the host -- taken from the ``_hw_list`` the transformer attaches to
+    ``value_spatial_shapes``.  Results are those of :class:`MSDeformAttnFunction`; geometries the tile kernel does not
+    cover fall through to the general kernel inside the extension (still CUDA -- there is no CPU path)."""
 
     @staticmethod
     def forward(ctx, value, value_spatial_shapes, sampling_locations, attention_weights, im2col_step):
         msda = ext.load()
         ctx.im2col_step = int(im2col_step)
         hw = [int(v) for pair in value_spatial_shapes._hw_list for v in pair]
+        ctx.hw = hw
+        tile = encoder_kernel_choice(msda, value, value_spatial_shapes, sampling_locations, attention_weights, hw,
+                                     ctx.im2col_step) == "tile"
         sink = _TIMING_SINK
         if sink is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        out = msda.ms_deform_attn_forward_enc(value, value_spatial_shapes, sampling_locations, attention_weights,
-                                              hw, ctx.im2col_step)
+        if tile:
+            out = msda.ms_deform_attn_forward_enc(value, value_spatial_shapes, sampling_locations, attention_weights,
+                                                  hw, ctx.im2col_step)
+        else:
+            out = msda.ms_deform_attn_forward(value, value_spatial_shapes, sampling_locations, attention_weights,
+                                              ctx.im2col_step)
         if sink is not None:
             e1.record()
             sink.append(("fwd", _dims(value, sampling_locations), e0, e1))
         ctx.save_for_backward(value, value_spatial_shapes, sampling_locations, attention_weights)
         return out
 
-    backward = MSDeformAttnFunction.backward
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        return _backward(ctx, grad_output, ctx.hw if _TILED_ENC_BWD else None)
 
 
 def ms_deform_attn(value: torch.Tensor, spatial_shapes: torch.Tensor, sampling_locations: torch.Tensor,

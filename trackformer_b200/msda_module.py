@@ -23,7 +23,6 @@ from torch import nn
 from .fused_linear import linear as fused_linear
 from .msda_function import MSDeformAttnEncFunction, MSDeformAttnFunction, MSDeformAttnFusedFunction
 
-_TILED_ENC = os.environ.get("TFB200_TILED_ENC", "0") == "1"
 # fold sampling_prep into the MSDeformAttn kernels (csrc/msda_run.cuh PREP variants); off until validated on a B200
 _FUSED_PREP = os.environ.get("TFB200_FUSED_PREP", "0") != "0"
 
@@ -158,9 +157,9 @@ class MSDeformAttn(nn.Module):
                 attn = attn.masked_fill(query_attn_mask[..., None, None, None], 0.0)
             locations = self._sampling_locations(reference_points, offsets, input_spatial_shapes)
 
-        if _TILED_ENC and hw is not None and len_q == len_in and value.is_cuda:
-            # encoder self-attention: queries are the pixels -> shared-memory tiled forward kernel (opt-in:
-            # bit-identical but currently slower than the direct kernel)
+        if hw is not None and len_q == len_in and value.is_cuda and value.dtype == torch.float32:
+            # encoder self-attention: queries are the pixels -> the TMA-staged tile kernel is a candidate (chosen per
+            # geometry by a one-time measurement, msda_function.encoder_kernel_choice)
             core = MSDeformAttnEncFunction
         else:
             core = MSDeformAttnFunction
