@@ -273,7 +273,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a collective that does not complete within two minutes is a bug, not a slow link: fail fast instead of holding
+        # N GPUs for the default ten minutes
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     tf32 = not args.no_tf32
     torch.backends.cuda.matmul.allow_tf32 = tf32
     torch.backends.cudnn.allow_tf32 = tf32
@@ -374,7 +377,8 @@ def main():
     #     by CUDA events on the launching stream; the launch counter gives the kernels per step.
     probe = TrainStep(model, criterion, None, use_graphs=False)
     probe(dev_frames, targets)
-    dense_flops = dense_flops_per_step(lambda: probe(dev_frames, targets)) if rank == 0 else None
+    # (every rank: the probe step issues the gradient collectives, so all ranks have to take it together)
+    dense_flops = dense_flops_per_step(lambda: probe(dev_frames, targets))
     sink = []
     msda_function.set_timing_sink(sink)
     launches0 = msda.launch_count()

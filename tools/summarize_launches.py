@@ -21,7 +21,7 @@ def family(name):
                      ("nchwToNhwc", "LIB cudnn layout"), ("convolve", "LIB cudnn conv"), ("nccl", "LIB nccl")):
         if key in n:
             return fam
-    m = re.search(r"native::(?:<unnamed>::)?(\w+)(?:<[^>]*?(\w+Functor|sum_functor|FillFunctor|direct_copy|Copy|neg_kernel|clamp|threshold|random)\w*)?", n)
+    m = re.search(r"(?:native|at)::(?:native::)?(?:<unnamed>::)?(\w+)(?:<[^>]*?(\w+Functor|sum_functor|FillFunctor|direct_copy|Copy|neg_kernel|clamp|threshold|random)\w*)?", n)
     if m:
         return "ATEN " + m.group(1) + (":" + m.group(2) if m.group(2) else "")
     return "OTHER " + re.sub(r"[<(].*", "", n)[:50]

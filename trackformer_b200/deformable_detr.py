@@ -24,6 +24,9 @@ def _clones(module, n):
     return nn.ModuleList([copy.deepcopy(module) for _ in range(n)])
 
 
+from .fused_linear import linear as fused_linear  # noqa: E402
+
+
 class MLP(nn.Module):
     """ReLU perceptron: ``num_layers`` Linear layers named ``layers.{i}``."""
 
@@ -35,7 +38,7 @@ class MLP(nn.Module):
 
     def forward(self, x):
         for i, layer in enumerate(self.layers):
-            x = layer(x)
+            x = fused_linear(x, layer.weight, layer.bias)
             if i + 1 < self.num_layers:
                 x = F.relu(x)
         return x

@@ -20,9 +20,9 @@ from torch import nn
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
-from . import ext
+from . import ext, seeds
 
-_MIN_ROWS = 2048          # below this the generic reduction is launch-bound anyway
+_MIN_ROWS = 64            # from here on the column-sum kernels beat the generic reduction (single launch up to 2048 rows)
 _SPLIT_K = os.environ.get("TFB200_WGRAD_SPLITK", "0") == "1"      # opt-in: see weight_grad
 _SM_COUNT = 148
 
@@ -70,7 +70,10 @@ _TCGEN05_PARTS = os.environ.get("TFB200_TCGEN05_PARTS", "w")
 def _tcgen05_ok(x, weight):
     if not (_TCGEN05 and torch.backends.cuda.matmul.allow_tf32 and x.is_contiguous() and weight.is_contiguous()):
         return False
-    return bool(ext.load().tf32_linear_supported(x.numel() // x.shape[-1], weight.shape[0], weight.shape[1]))
+    rows = x.numel() // x.shape[-1]
+    if rows < 2048:                      # decoder-sized products: the library is as fast (gemm_bench, M = 300)
+        return False
+    return bool(ext.load().tf32_linear_supported(rows, weight.shape[0], weight.shape[1]))
 
 
 class _LinearColsum(Function):
@@ -120,7 +123,7 @@ class _ReluDropout(Function):
         keep = 1.0 - p
         seed = None
         if training:
-            seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=a.device)
+            seed = seeds.next_seed(a.device)
         h = m.relu_dropout_forward(a, seed, keep, training)
         ctx.save_for_backward(h)
         ctx.keep, ctx.training = keep, training
@@ -135,7 +138,7 @@ class _ReluDropout(Function):
 
 def relu_dropout(a: torch.Tensor, dropout: nn.Dropout) -> torch.Tensor:
     """``dropout(relu(a))``."""
-    if a.is_cuda and a.dtype == torch.float32 and a.numel() % 4 == 0 and a.numel() >= 4 * _MIN_ROWS:
+    if a.is_cuda and a.dtype == torch.float32 and a.numel() % 4 == 0 and a.numel() >= 8192:
         training = bool(dropout.training and dropout.p > 0.0)
         return _ReluDropout.apply(a, float(dropout.p), training)
     return dropout(F.relu(a))

@@ -16,7 +16,7 @@ from torch import nn
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
-from . import ext
+from . import ext, seeds
 
 # mask-free dropout (hash of a per-call device seed and the element index, like fused_linear.relu_dropout) instead of a
 # bernoulli_ mask tensor per call; TFB200_LN_SEEDED=0 keeps the mask route
@@ -27,7 +27,7 @@ class _AddDropoutLayerNormSeeded(Function):
     @staticmethod
     def forward(ctx, x, branch, gamma, beta, p, eps):
         keep = 1.0 - p
-        seed = torch.randint(0, 2 ** 62, (1,), dtype=torch.int64, device=x.device)
+        seed = seeds.next_seed(x.device)
         y, s, mean, rstd = ext.load().add_dropout_layernorm_seeded_forward(x, branch, seed, gamma, beta, keep, eps)
         ctx.save_for_backward(s, mean, rstd, gamma, seed)
         ctx.keep = keep
