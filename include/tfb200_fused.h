@@ -153,6 +153,22 @@ int tfb200_set_loss_bwd_f32(const float* unit_logits, const float* unit_l1, cons
                             const float* g_l1, const float* g_giou, const float* num_boxes, float* grad_logits,
                             float* grad_boxes, int K, int B, int Q, int C, void* stream);
 
+/* Dense self-attention over a few hundred positions, 32 channels per head (csrc/small_attn.cu; replaces the core of the
+ * decoder's nn.MultiheadAttention, reference models/deformable_transformer.py:342,366-368).  q / k / v / out (and dout /
+ * dq / dk / dv) are [L][B][H][32] VIEWS: channel stride 1, head stride 32, sequence / batch strides (in elements) in
+ *   strides8  = {q_l, q_b, k_l, k_b, v_l, v_b, out_l, out_b}
+ *   strides16 = strides8 + {dout_l, dout_b, dq_l, dq_b, dk_l, dk_b, dv_l, dv_b}
+ * out = dropout(softmax(scale * q k^T + mask)) v; key_pad [B][L] (1 = ignore that key) or NULL; seed_dev NULL = no
+ * dropout, else keep_prob in (0, 1] with the mask-free hash RNG; lse [B][H][L] (saved for the backward);
+ * delta_ws [B][H][L] scratch.                                                                                       */
+int tfb200_small_attn_fwd_f32(const float* q, const float* k, const float* v, const uint8_t* key_pad,
+                              const int64_t* seed_dev, float* out, float* lse, int B, int H, int L,
+                              const int64_t* strides8, float scale, float keep_prob, void* stream);
+int tfb200_small_attn_bwd_f32(const float* q, const float* k, const float* v, const uint8_t* key_pad,
+                              const int64_t* seed_dev, const float* out, const float* lse, const float* dout,
+                              float* dq, float* dk, float* dv, float* delta_ws, int B, int H, int L,
+                              const int64_t* strides16, float scale, float keep_prob, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -368,6 +368,71 @@ at::Tensor tf32_linear_wgrad(const at::Tensor& dy, const at::Tensor& x) {
   return dw;
 }
 
+// Dense self-attention of the decoder queries (csrc/small_attn.cu): q, k, v are [L, B, H, 32] views (channel stride 1,
+// head stride 32); key_pad [B, L] bool or None; seed None = no dropout.  Returns {out [L, B, H, 32], lse [B, H, L]}.
+static void check_view(const at::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kFloat && t.dim() == 4 && t.size(3) == 32 && t.stride(3) == 1 &&
+                  t.stride(2) == 32 && (reinterpret_cast<uintptr_t>(t.data_ptr()) & 15u) == 0 && t.stride(0) % 4 == 0 &&
+                  t.stride(1) % 4 == 0,
+              "small_attention: ", name, " must be an fp32 CUDA [L, B, H, 32] view with 16-byte aligned rows");
+}
+std::vector<at::Tensor> small_attention_forward(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
+                                                const c10::optional<at::Tensor>& key_pad,
+                                                const c10::optional<at::Tensor>& seed, double scale, double keep_prob) {
+  check_view(q, "q"); check_view(k, "k"); check_view(v, "v");
+  const int64_t L = q.size(0), B = q.size(1), H = q.size(2);
+  TORCH_CHECK(k.sizes() == q.sizes() && v.sizes() == q.sizes(), "small_attention: q, k, v must have the same shape");
+  const c10::cuda::CUDAGuard guard(q.device());
+  at::Tensor out = at::empty({L, B, H, 32}, q.options());
+  at::Tensor lse = at::empty({B, H, L}, q.options());
+  const uint8_t* kp = nullptr;
+  at::Tensor kpc;
+  if (key_pad.has_value() && key_pad->defined()) {
+    kpc = key_pad->contiguous();
+    TORCH_CHECK(kpc.numel() == B * L && kpc.element_size() == 1, "small_attention: key_pad must be a bool [B, L] tensor");
+    kp = static_cast<const uint8_t*>(kpc.data_ptr());
+  }
+  const int64_t* sp = (seed.has_value() && seed->defined()) ? seed->data_ptr<int64_t>() : nullptr;
+  const int64_t st[8] = {q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1), out.stride(0), out.stride(1)};
+  const int rc = tfb200_small_attn_fwd_f32(q.data_ptr<float>(), k.data_ptr<float>(), v.data_ptr<float>(), kp, sp,
+                                           out.data_ptr<float>(), lse.data_ptr<float>(), int(B), int(H), int(L), st,
+                                           float(scale), float(keep_prob), c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "small_attention_forward failed (code ", rc, ")");
+  return {out, lse};
+}
+
+std::vector<at::Tensor> small_attention_backward(const at::Tensor& q, const at::Tensor& k, const at::Tensor& v,
+                                                 const c10::optional<at::Tensor>& key_pad,
+                                                 const c10::optional<at::Tensor>& seed, const at::Tensor& out,
+                                                 const at::Tensor& lse, const at::Tensor& grad_out, double scale,
+                                                 double keep_prob) {
+  check_view(q, "q"); check_view(k, "k"); check_view(v, "v"); check_view(out, "out");
+  const at::Tensor go = grad_out.contiguous();
+  check_view(go, "grad_out");
+  const int64_t L = q.size(0), B = q.size(1), H = q.size(2);
+  const c10::cuda::CUDAGuard guard(q.device());
+  at::Tensor dq = at::empty({L, B, H, 32}, q.options()), dk = at::empty({L, B, H, 32}, q.options()),
+             dv = at::empty({L, B, H, 32}, q.options());
+  at::Tensor delta = at::empty({B, H, L}, q.options());
+  const uint8_t* kp = nullptr;
+  at::Tensor kpc;
+  if (key_pad.has_value() && key_pad->defined()) {
+    kpc = key_pad->contiguous();
+    kp = static_cast<const uint8_t*>(kpc.data_ptr());
+  }
+  const int64_t* sp = (seed.has_value() && seed->defined()) ? seed->data_ptr<int64_t>() : nullptr;
+  const int64_t st[16] = {q.stride(0), q.stride(1), k.stride(0), k.stride(1), v.stride(0), v.stride(1), out.stride(0),
+                          out.stride(1), go.stride(0), go.stride(1), dq.stride(0), dq.stride(1), dk.stride(0), dk.stride(1),
+                          dv.stride(0), dv.stride(1)};
+  const int rc = tfb200_small_attn_bwd_f32(q.data_ptr<float>(), k.data_ptr<float>(), v.data_ptr<float>(), kp, sp,
+                                           out.data_ptr<float>(), lse.data_ptr<float>(), go.data_ptr<float>(),
+                                           dq.data_ptr<float>(), dk.data_ptr<float>(), dv.data_ptr<float>(),
+                                           delta.data_ptr<float>(), int(B), int(H), int(L), st, float(scale),
+                                           float(keep_prob), c10::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "small_attention_backward failed (code ", rc, ")");
+  return {dq, dk, dv};
+}
+
 // boxes = sigmoid(delta + inverse_sigmoid(ref)) (csrc/box_refine.cu); delta [..., 4], ref [..., 2 or 4]
 at::Tensor refine_boxes_forward(const at::Tensor& delta, const at::Tensor& ref, double eps) {
   TORCH_CHECK(delta.is_cuda() && ref.is_cuda() && delta.scalar_type() == at::kFloat && ref.scalar_type() == at::kFloat &&
@@ -686,6 +751,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_loss_backward", &set_loss_backward);
   m.def("sampling_prep_forward", &sampling_prep_forward);
   m.def("sampling_prep_backward", &sampling_prep_backward);
+  m.def("small_attention_forward", &small_attention_forward);
+  m.def("small_attention_backward", &small_attention_backward);
   m.def("refine_boxes_forward", &refine_boxes_forward);
   m.def("refine_boxes_backward", &refine_boxes_backward);
   m.def("tf32_linear", &tf32_linear);

@@ -22,7 +22,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from . import seeds
+from . import seeds, small_attention
 from .fused_linear import linear as fused_linear, relu_dropout
 from .fused_norm import add_dropout_layernorm
 from .msda_module import MSDeformAttn
@@ -151,8 +151,11 @@ class DeformableTransformerDecoderLayer(nn.Module):
         # need_weights=False: the averaged attention map is never used (the reference discards it too,
         # deformable_transformer.py:368) and asking for it forces the unfused bmm / softmax / bmm path with ~25 small
         # launches per layer and direction; without it the module runs one fused attention kernel
-        sa = self.self_attn(qk, qk, tgt.transpose(0, 1), key_padding_mask=key_mask,
-                            need_weights=_MHA_NEED_WEIGHTS)[0].transpose(0, 1)
+        if small_attention.supported(self.self_attn, qk) and not _MHA_NEED_WEIGHTS:
+            sa = small_attention.mha_forward(self.self_attn, qk, tgt.transpose(0, 1), key_mask).transpose(0, 1)
+        else:
+            sa = self.self_attn(qk, qk, tgt.transpose(0, 1), key_padding_mask=key_mask,
+                                need_weights=_MHA_NEED_WEIGHTS)[0].transpose(0, 1)
         tgt = add_dropout_layernorm(tgt, sa, self.dropout2, self.norm2)
         # deformable cross-attention into the encoder memory
         ca = self.cross_attn(_add_pos(tgt, query_pos), reference_points, src, src_spatial_shapes,
