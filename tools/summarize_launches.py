@@ -15,6 +15,9 @@ def family(name):
         r"refine_boxes|detect_postprocess|finish)\w*)", n)
     if own and "native::<unnamed>" not in n:
         return "OWN " + own.group(1)
+    anon = re.match(r"(?:void )?<unnamed>::(\w+)", n)           # kernels of libmsda_b200.so in anonymous namespaces
+    if anon:
+        return "OWN " + anon.group(1)
     for key, fam in (("cutlass_80", "LIB cublas sm80 mma.sync gemm (cutlass_80 s1688)"), ("cutlass3x", "LIB cutlass3x sm100 gemm/conv"),
                      ("cutlass", "LIB cutlass other"), ("cudnn", "LIB cudnn"), ("xmma", "LIB cudnn xmma"),
                      ("fmha", "LIB fused attention (sdpa, sm80 kernel)"), ("cublas", "LIB cublas misc"),

@@ -32,6 +32,14 @@ constexpr int kEbThreads = 256;
 // derivative sign codes: 0 -> 0, 1 -> +1, 2 -> -1
 __device__ __forceinline__ unsigned eb_enc(float d) { return d > 0.f ? 1u : (d < 0.f ? 2u : 0u); }
 __device__ __forceinline__ float eb_dec(unsigned c) { return (c & 1u) ? 1.f : ((c & 2u) ? -1.f : 0.f); }
+// all four signs of a tap at once: one indexed 128-bit constant load instead of ~20 select instructions per step
+struct EbSigns { float4 v[256]; };
+__host__ __device__ constexpr float eb_dec_c(unsigned c) { return (c & 1u) ? 1.f : ((c & 2u) ? -1.f : 0.f); }
+__constant__ EbSigns kEbSigns;
+inline void eb_fill_signs(EbSigns* t) {
+  for (unsigned c = 0; c < 256; ++c)
+    t->v[c] = make_float4(eb_dec_c(c), eb_dec_c(c >> 2), eb_dec_c(c >> 4), eb_dec_c(c >> 6));
+}
 
 __device__ __forceinline__ u64 fmul2(u64 a, u64 b) {
   u64 d;
@@ -57,9 +65,31 @@ __device__ __forceinline__ void red2(float* p, const u64 (&v)[2]) {
       : "memory");
 }
 
+// predicated helpers (straight-line code: the flush / reset decisions are per 8-lane group, branches would diverge)
+__device__ __forceinline__ void red2_if(const float* p, const u64 (&v)[2], bool pred) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .f32 a, b, c, d;\n\tsetp.ne.b32 p, %3, 0;\n\tmov.b64 {a, b}, %1;\n\tmov.b64 {c, d}, %2;\n\t"
+      "@p red.relaxed.gpu.global.add.v4.f32 [%0], {a, b, c, d};\n\t}" ::"l"(p), "l"(v[0]), "l"(v[1]), "r"(int(pred))
+      : "memory");
+}
+// acc = acc * keep + k * g  (keep = 0 right after the set was flushed, else 1; both lanes of the f32x2).  Arithmetic
+// instead of a select: ptxas turns a predicated mul / fma pair into both products plus two SELs per register pair.
+__device__ __forceinline__ void acc2(u64& acc, float k, u64 g, float keep) {
+  u64 kk, kp;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(kk) : "f"(k));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(kp) : "f"(keep));
+  const u64 t = fmul2(kk, g);
+  asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc) : "l"(kp), "l"(t));
+}
+
 // One sample slot of one level for one warp: the run of R queries, forward values + all three gradients.
 //   staged (GLOBAL = false): s_o = rowA | rowB << 9 | codes << 18 (0x1FF = keep the set)
 //   global (GLOBAL = true) : s_o = pixel of the NEW right column | load A << 20 | load B << 21 | reload << 22 | codes << 23
+// First version: 190 SASS instructions per step (ncu: 164 M per C2 call, issue bound) -- 25 of them re-deriving the
+// grad_output address from the thread index every step (rematerialised under the 128-register cap), ~50 in the two
+// divergent flush branches with their register copies, 16 in 64-bit reduction addresses.  Now: the grad_output pointer is
+// an opaque register pair that only gets incremented, flush / reset are predicated instructions, addresses are 32-bit
+// offsets + one mad.wide each.
 template <bool GLOBAL>
 __device__ __forceinline__ void eb_slot_pass(uint32_t sw_addr, uint32_t sa_addr, uint32_t so_addr, uint32_t slot, float4* s_w_e0,
                                              uint32_t bufa, uint32_t pitch, int BW, unsigned gbox, const float* vh, float* gvh,
@@ -71,6 +101,9 @@ __device__ __forceinline__ void eb_slot_pass(uint32_t sw_addr, uint32_t sa_addr,
   unsigned gA = 0u, gB = 0u;                                     // element offsets of the rows the pending sums belong to
   int nzA = 0, nzB = 0;                                          // OR of the coefficient bits seen since the last flush
   const unsigned magic = (65536u + unsigned(BW) - 1u) / unsigned(BW);
+  const float* gp = gout0;
+  asm volatile("" : "+l"(gp));                                   // opaque: keep the pointer, do not rematerialise it
+  const size_t gstep = size_t(gq_stride) * 4;
 
   float4 wn;
   float an;
@@ -81,9 +114,11 @@ __device__ __forceinline__ void eb_slot_pass(uint32_t sw_addr, uint32_t sa_addr,
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(wn.x), "=f"(wn.y), "=f"(wn.z), "=f"(wn.w) : "r"(sw_addr + eo * 16u));
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(an) : "r"(sa_addr + eo * 4u));
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(on) : "r"(so_addr + eo * 4u));
-    gn[0] = gn[1] = 0ull;
-    if ((valid_mask >> r) & 1u)
-      asm volatile("ld.global.nc.v2.b64 {%0, %1}, [%2];" : "=l"(gn[0]), "=l"(gn[1]) : "l"(gout0 + size_t(r) * gq_stride));
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\tmov.b64 %0, 0;\n\tmov.b64 %1, 0;\n\t"
+                 "@p ld.global.nc.v2.b64 {%0, %1}, [%2];\n\t}"
+                 : "=l"(gn[0]), "=l"(gn[1])
+                 : "l"(gp), "r"(int((valid_mask >> r) & 1u)));
+    gp = reinterpret_cast<const float*>(reinterpret_cast<const char*>(gp) + gstep);
   };
   fetch(0);
   float part[12];
@@ -114,13 +149,14 @@ __device__ __forceinline__ void eb_slot_pass(uint32_t sw_addr, uint32_t sa_addr,
       ngA = reload ? gr : (la ? gB + gstride : gA);
       ngB = reload ? gr + gstride : (lb ? gA + gstride : gB);
     }
-    if (la) {
-      if ((unsigned(nzA) << 1) != 0u) { red2(gvh + gA, GA1); red2(gvh + gA + rowpitch, GA3); }
-      GA1[0] = GA1[1] = GA3[0] = GA3[1] = 0ull; nzA = 0;
+    // a set that is about to be reloaded first sends what it has collected for its old rows
+    if (la && (unsigned(nzA) << 1) != 0u) {
+      red2(const_cast<float*>(row_ptr(gvh, gA)), GA1);
+      red2(const_cast<float*>(row_ptr(gvh, gA + rowpitch)), GA3);
     }
-    if (lb) {
-      if ((unsigned(nzB) << 1) != 0u) { red2(gvh + gB, GB1); red2(gvh + gB + rowpitch, GB3); }
-      GB1[0] = GB1[1] = GB3[0] = GB3[1] = 0ull; nzB = 0;
+    if (lb && (unsigned(nzB) << 1) != 0u) {
+      red2(const_cast<float*>(row_ptr(gvh, gB)), GB1);
+      red2(const_cast<float*>(row_ptr(gvh, gB + rowpitch)), GB3);
     }
     gA = ngA; gB = ngB;
     if (GLOBAL) {
@@ -137,7 +173,8 @@ __device__ __forceinline__ void eb_slot_pass(uint32_t sw_addr, uint32_t sa_addr,
     }
 
     // w = (x-weight of set A, x-weight of set B, y-weight of the top row, y-weight of the bottom row)
-    const float dA = eb_dec(codes), dB = eb_dec(codes >> 2), dya = eb_dec(codes >> 4), dyb = eb_dec(codes >> 6);
+    const float4 sg = kEbSigns.v[codes & 0xFFu];
+    const float dA = sg.x, dB = sg.y, dya = sg.z, dyb = sg.w;
     const float e1 = dot2(g, A1), e3 = dot2(g, A3), f1 = dot2(g, B1), f3 = dot2(g, B3);
     const float T = fmaf(w.x, e1, w.y * f1), Bo = fmaf(w.x, e3, w.y * f3);          // g . top / bottom interpolant
     const float DT = fmaf(dA, e1, dB * f1), DB = fmaf(dA, e3, dB * f3);            // g . d/dx of them
@@ -146,12 +183,13 @@ __device__ __forceinline__ void eb_slot_pass(uint32_t sw_addr, uint32_t sa_addr,
     part[3 * (r & 3) + 2] = fmaf(dya, T, dyb * Bo) * a * fH;
     const float ya = w.z * a, yb = w.w * a;
     const float kA1 = ya * w.x, kA3 = yb * w.x, kB1 = ya * w.y, kB3 = yb * w.y;
-    ffma2(GA1[0], kA1, g[0]); ffma2(GA1[1], kA1, g[1]);
-    ffma2(GA3[0], kA3, g[0]); ffma2(GA3[1], kA3, g[1]);
-    ffma2(GB1[0], kB1, g[0]); ffma2(GB1[1], kB1, g[1]);
-    ffma2(GB3[0], kB3, g[0]); ffma2(GB3[1], kB3, g[1]);
-    nzA |= __float_as_int(kA1) | __float_as_int(kA3);
-    nzB |= __float_as_int(kB1) | __float_as_int(kB3);
+    const float keepA = la ? 0.f : 1.f, keepB = lb ? 0.f : 1.f;
+    acc2(GA1[0], kA1, g[0], keepA); acc2(GA1[1], kA1, g[1], keepA);
+    acc2(GA3[0], kA3, g[0], keepA); acc2(GA3[1], kA3, g[1], keepA);
+    acc2(GB1[0], kB1, g[0], keepB); acc2(GB1[1], kB1, g[1], keepB);
+    acc2(GB3[0], kB3, g[0], keepB); acc2(GB3[1], kB3, g[1], keepB);
+    nzA = (nzA & (int(la) - 1)) | __float_as_int(kA1) | __float_as_int(kA3);
+    nzB = (nzB & (int(lb) - 1)) | __float_as_int(kB1) | __float_as_int(kB3);
 
     if ((r & 3) == 3) {
       float r3[3];
@@ -162,8 +200,14 @@ __device__ __forceinline__ void eb_slot_pass(uint32_t sw_addr, uint32_t sa_addr,
       }
     }
   }
-  if ((unsigned(nzA) << 1) != 0u) { red2(gvh + gA, GA1); red2(gvh + gA + rowpitch, GA3); }
-  if ((unsigned(nzB) << 1) != 0u) { red2(gvh + gB, GB1); red2(gvh + gB + rowpitch, GB3); }
+  if ((unsigned(nzA) << 1) != 0u) {
+    red2(const_cast<float*>(row_ptr(gvh, gA)), GA1);
+    red2(const_cast<float*>(row_ptr(gvh, gA + rowpitch)), GA3);
+  }
+  if ((unsigned(nzB) << 1) != 0u) {
+    red2(const_cast<float*>(row_ptr(gvh, gB)), GB1);
+    red2(const_cast<float*>(row_ptr(gvh, gB + rowpitch)), GB3);
+  }
 }
 
 __global__ void __launch_bounds__(kEbThreads, 2)

@@ -22,6 +22,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <mutex>
 
 #include "../../include/msda_b200.h"
 #include "launch_counter.h"
@@ -816,6 +817,16 @@ int msda_b200_backward_enc_tiled_f32(const float* value, const int64_t* spatial_
   cudaStream_t st = cudaStream_t(stream);
   cudaError_t e = cudaMemsetAsync(grad_value, 0, sizeof(float) * size_t(N) * S * M * D, st);
   if (e != cudaSuccess) return int(e);
+  {
+    static std::once_flag signs_once;
+    static cudaError_t signs_rc = cudaSuccess;
+    std::call_once(signs_once, [] {
+      EbSigns t;
+      eb_fill_signs(&t);
+      signs_rc = cudaMemcpyToSymbol(kEbSigns, &t, sizeof(t));     // (per device context: one GPU per process)
+    });
+    if (signs_rc != cudaSuccess) return int(signs_rc);
+  }
   MSDA_ENSURE_SMEM(msda_bwd_enc_tma_kernel, kEbSmemBytes);
   msda_bwd_enc_tma_kernel<<<unsigned(grid), kEbThreads, kEbSmemBytes, st>>>(value, sampling_loc, attn_weight, grad_output,
                                                                            grad_value, grad_sampling_loc, grad_attn_weight, g,

@@ -84,8 +84,9 @@ def _backward(ctx, grad_output, hw):
 import os as _os
 
 _TILED_ENC = _os.environ.get("TFB200_TILED_ENC", "auto")            # "auto" | "1" (always tile) | "0" (never)
-_TILED_ENC_BWD = _os.environ.get("TFB200_TILED_ENC_BWD", "0") == "1"  # opt-in: correct, not yet faster
+_TILED_ENC_BWD = _os.environ.get("TFB200_TILED_ENC_BWD", "auto")     # the same three modes for the backward tile kernel
 _ENC_CHOICE = {}
+_ENC_BWD_CHOICE = {}
 
 
 def _time_us(fn, iters=3):
@@ -110,6 +111,22 @@ def encoder_kernel_choice(msda, value, shapes, loc, attn, hw, step):
         t_tile = _time_us(lambda: msda.ms_deform_attn_forward_enc(value, shapes, loc, attn, hw, step))
         t_direct = _time_us(lambda: msda.ms_deform_attn_forward(value, shapes, loc, attn, step))
         choice = _ENC_CHOICE[key] = "tile" if t_tile < 0.97 * t_direct else "direct"
+    return choice
+
+
+def encoder_backward_choice(msda, value, shapes, loc, attn, grad_out, hw, step):
+    """Same one-time measurement for the backward (C2 encoder call on B200: grid pattern 218 vs 235 us, +-0.5 px jitter
+    302 vs 245 us)."""
+    if _TILED_ENC_BWD in ("0", "1"):
+        return "tile" if _TILED_ENC_BWD == "1" else "direct"
+    key = (tuple(value.shape), tuple(hw), value.device.index)
+    choice = _ENC_BWD_CHOICE.get(key)
+    if choice is None:
+        if torch.cuda.is_current_stream_capturing():
+            return "direct"
+        t_tile = _time_us(lambda: msda.ms_deform_attn_backward_enc(value, shapes, loc, attn, grad_out, hw, step))
+        t_direct = _time_us(lambda: msda.ms_deform_attn_backward(value, shapes, loc, attn, grad_out, step))
+        choice = _ENC_BWD_CHOICE[key] = "tile" if t_tile < 0.97 * t_direct else "direct"
     return choice
 
 
@@ -146,7 +163,10 @@ class MSDeformAttnEncFunction(Function):
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_output):
-        return _backward(ctx, grad_output, ctx.hw if _TILED_ENC_BWD else None)
+        value, shapes, loc, attn = ctx.saved_tensors
+        tile = encoder_backward_choice(ext.load(), value, shapes, loc, attn, grad_output.contiguous(), ctx.hw,
+                                       ctx.im2col_step) == "tile"
+        return _backward(ctx, grad_output, ctx.hw if tile else None)
 
 
 def ms_deform_attn(value: torch.Tensor, spatial_shapes: torch.Tensor, sampling_locations: torch.Tensor,
