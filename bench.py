@@ -274,6 +274,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         import datetime
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's banner must not land in front of the JSON line
         # a collective that does not complete within two minutes is a bug, not a slow link: fail fast instead of holding
         # N GPUs for the default ten minutes
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
