@@ -153,6 +153,11 @@ int tfb200_set_loss_bwd_f32(const float* unit_logits, const float* unit_l1, cons
                             const float* g_l1, const float* g_giou, const float* num_boxes, float* grad_logits,
                             float* grad_boxes, int K, int B, int Q, int C, void* stream);
 
+/* Stem of the ResNet trunk in one pass (csrc/frozen_bn_act.cu): y = maxpool 3x3 / stride 2 / pad 1 of
+ * relu(x * scale[c] + shift[c]); x [N][H][W][C] channels-last, y [N][(H+1)/2][(W+1)/2][C]; forward only (frozen stem). */
+int tfb200_frozen_bn_relu_maxpool_f32(const float* x, const float* scale, const float* shift, float* y, int N, int H, int W,
+                                      int C, void* stream);
+
 /* Dense self-attention over a few hundred positions, 32 channels per head (csrc/small_attn.cu; replaces the core of the
  * decoder's nn.MultiheadAttention, reference models/deformable_transformer.py:342,366-368).  q / k / v / out (and dout /
  * dq / dk / dv) are [L][B][H][32] VIEWS: channel stride 1, head stride 32, sequence / batch strides (in elements) in

@@ -4,6 +4,7 @@ import copy
 
 import pytest
 import torch
+import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
@@ -70,3 +71,18 @@ def test_patched_trunk_equals_unpatched_on_gpu(cuda_device, monkeypatch):
     gb = torch.autograd.grad(sum(v.square().mean() for v in b.values()), pb)
     for u, v in zip(ga, gb):
         torch.testing.assert_close(u, v, rtol=1e-3, atol=1e-3 * float(v.abs().max()))
+
+
+@pytest.mark.parametrize("shape", [(1, 64, 45, 67), (2, 64, 80, 112), (1, 8, 1, 1), (1, 64, 400, 667)])
+def test_stem_bn_relu_maxpool_kernel(cuda_device, shape):
+    """bn1 + relu + maxpool(3, 2, 1) of the frozen stem in one pass against the PyTorch chain (odd sizes: the last
+    window row / column hangs over the border; negative scales: max must be taken AFTER the affine map)."""
+    from trackformer_b200 import ext
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(shape, generator=g).to(cuda_device).contiguous(memory_format=torch.channels_last)
+    scale = (torch.randn(shape[1], generator=g) * 1.5).to(cuda_device)
+    shift = torch.randn(shape[1], generator=g).to(cuda_device)
+    y = ext.load().frozen_bn_relu_maxpool(x, scale, shift)
+    ref = F.max_pool2d(F.relu(x * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)), 3, 2, 1)
+    assert y.shape == ref.shape and y.is_contiguous(memory_format=torch.channels_last)
+    torch.testing.assert_close(y, ref, rtol=1e-6, atol=1e-6)

@@ -106,12 +106,24 @@ class _Trunk(nn.ModuleDict):
         collected = {}
         fuse_stem = getattr(self, "fused_bn", False)
         cut = self.cut
+        skip_pool = False
         for name, stage in self.items():
             if fuse_stem and name == "bn1":
-                from .fused_bn import bn_act
-                x = bn_act(x, stage, True)             # stem: bn1 + relu in one pass
+                from .fused_bn import bn_act, fusable
+                pool = self["maxpool"] if "maxpool" in self else None
+                if (pool is not None and not x.requires_grad and fusable(x) and pool.kernel_size == 3 and pool.stride == 2
+                        and pool.padding == 1 and pool.dilation == 1 and not pool.ceil_mode):
+                    # frozen stem (reference backbone.py:64-68): bn1 + relu + maxpool as one forward-only pass
+                    from . import ext
+                    scale, shift = stage.affine()
+                    x = ext.load().frozen_bn_relu_maxpool(x, scale, shift)
+                    skip_pool = True
+                else:
+                    x = bn_act(x, stage, True)         # stem: bn1 + relu in one pass
                 continue
             if fuse_stem and name == "relu":
+                continue
+            if skip_pool and name == "maxpool":
                 continue
             x = stage(x)
             key = self.taps.get(name)

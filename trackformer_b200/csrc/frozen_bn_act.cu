@@ -59,6 +59,40 @@ frozen_bn_act_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict
   }
 }
 
+// Stem of the trunk in one pass: y = maxpool3x3/s2/p1(relu(x * scale + shift)) (torchvision resnet: bn1 -> relu ->
+// maxpool; reference backbone.py:70-78).  Forward only -- the stem is frozen (backbone.py:64-68), nothing upstream needs
+// a gradient.  Thread = output pixel x 4 channels; padding contributes nothing (max over the in-bounds taps, like
+// PyTorch's -inf padding).
+__global__ void __launch_bounds__(kThreads)
+frozen_bn_relu_maxpool_kernel(const float4* __restrict__ x, const float4* __restrict__ scale, const float4* __restrict__ shift,
+                              float4* __restrict__ y, int N, int H, int W, int Ho, int Wo, int cpacks) {
+  const int64_t total = int64_t(N) * Ho * Wo * cpacks;
+  const int64_t stride = int64_t(gridDim.x) * kThreads;
+  for (int64_t i = int64_t(blockIdx.x) * kThreads + threadIdx.x; i < total; i += stride) {
+    const int c = int(i % cpacks);
+    int64_t p = i / cpacks;
+    const int xo = int(p % Wo); p /= Wo;
+    const int yo = int(p % Ho);
+    const int n = int(p / Ho);
+    const float4 s = __ldg(scale + c), b = __ldg(shift + c);
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f);                 // relu(.) >= 0 and every window has an in-bounds tap
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int yi = 2 * yo + dy;
+      if (yi < 0 || yi >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int xi = 2 * xo + dx;
+        if (xi < 0 || xi >= W) continue;
+        const float4 v = __ldg(x + ((int64_t(n) * H + yi) * W + xi) * cpacks + c);
+        m.x = fmaxf(m.x, fmaf(v.x, s.x, b.x)); m.y = fmaxf(m.y, fmaf(v.y, s.y, b.y));
+        m.z = fmaxf(m.z, fmaf(v.z, s.z, b.z)); m.w = fmaxf(m.w, fmaf(v.w, s.w, b.w));
+      }
+    }
+    y[i] = m;
+  }
+}
+
 inline bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
 
 inline unsigned grid_for(int64_t npacks) {
@@ -119,4 +153,18 @@ int tfb200_frozen_bn_act_bwd_f32(const float* dy, const float* y, const float* s
   return int(cudaGetLastError());
 }
 
+
+int tfb200_frozen_bn_relu_maxpool_f32(const float* x, const float* scale, const float* shift, float* y, int N, int H, int W,
+                                      int C, void* stream) {
+  if (!x || !scale || !shift || !y) return TFB200_E_NULLPTR;
+  if (N < 1 || H < 1 || W < 1 || C <= 0 || C % 4 != 0) return TFB200_E_SHAPE;
+  if (misaligned(x) || misaligned(y) || misaligned(scale) || misaligned(shift)) return TFB200_E_SHAPE;
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t total = int64_t(N) * Ho * Wo * (C / 4);
+  frozen_bn_relu_maxpool_kernel<<<grid_for(total), kThreads, 0, cudaStream_t(stream)>>>(
+      reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(scale), reinterpret_cast<const float4*>(shift),
+      reinterpret_cast<float4*>(y), N, H, W, Ho, Wo, C / 4);
+  msda_b200_count_launches(1);
+  return int(cudaGetLastError());
+}
 }  // extern "C"

@@ -287,16 +287,18 @@ colsum_small_kernel(const float* __restrict__ x, float* __restrict__ out, int ro
   __shared__ float red[8][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
-  float a0 = 0.f, a1 = 0.f;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (c < C) {
     int r = w;
-    for (; r + 8 < rows; r += 16) {
+    for (; r + 24 < rows; r += 32) {                  // four independent loads in flight per lane
       a0 += __ldg(x + size_t(r) * C + c);
       a1 += __ldg(x + size_t(r + 8) * C + c);
+      a2 += __ldg(x + size_t(r + 16) * C + c);
+      a3 += __ldg(x + size_t(r + 24) * C + c);
     }
-    if (r < rows) a0 += __ldg(x + size_t(r) * C + c);
+    for (; r < rows; r += 8) a0 += __ldg(x + size_t(r) * C + c);
   }
-  red[w][lane] = a0 + a1;
+  red[w][lane] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (w == 0 && c < C) {
     float t = 0.f;

@@ -258,9 +258,17 @@ static Family pick_family(int variant, int64_t groups, const struct Dims& d);
       value, shapes, loc, attn, gout, gval, gloc, gattn, d.S, d.M, d.D, d.L, d.Lq, d.P, groups)
 
 // Strip length (iterations of 32 groups) per CTA for the d32 kernels: keep at least ~2 waves of CTAs in
-// flight on 148 SMs, but let big problems walk contiguous strips so neighbouring queries share L1 lines.
+// flight on the device's SMs (148 on a B200), but let big problems walk contiguous strips so neighbouring queries share L1 lines.
 static int pick_iters(int64_t ctas) {
-  const int64_t two_waves = 148 * 8 * 2;
+  static std::atomic<int> sms{0};
+  int n = sms.load(std::memory_order_relaxed);
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    sms.store(n, std::memory_order_relaxed);
+  }
+  const int64_t two_waves = int64_t(n) * 8 * 2;
   int it = int(ctas / two_waves);
   return it < 1 ? 1 : (it > 8 ? 8 : it);
 }

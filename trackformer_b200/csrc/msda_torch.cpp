@@ -664,6 +664,21 @@ at::Tensor frozen_bn_act_forward(const at::Tensor& x, const c10::optional<at::Te
   return y;
 }
 
+at::Tensor frozen_bn_relu_maxpool(const at::Tensor& x, const at::Tensor& scale, const at::Tensor& shift) {
+  TORCH_CHECK(nhwc_dense(x), "frozen_bn_relu_maxpool: x must be a channels-last fp32 CUDA tensor [N,C,H,W]");
+  const int64_t N = x.size(0), C = x.size(1), H = x.size(2), W = x.size(3);
+  TORCH_CHECK(C % 4 == 0 && scale.numel() == C && shift.numel() == C && scale.is_cuda() && shift.is_cuda() &&
+              scale.scalar_type() == at::kFloat && shift.scalar_type() == at::kFloat, "frozen_bn_relu_maxpool: bad scale/shift");
+  const c10::cuda::CUDAGuard guard(x.device());
+  auto sc = scale.contiguous().view({C}), sh = shift.contiguous().view({C});
+  auto y = at::empty({N, C, (H + 1) / 2, (W + 1) / 2}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+  const int rc = tfb200_frozen_bn_relu_maxpool_f32(x.data_ptr<float>(), sc.data_ptr<float>(), sh.data_ptr<float>(),
+                                                   y.data_ptr<float>(), int(N), int(H), int(W), int(C),
+                                                   at::cuda::getCurrentCUDAStream().stream());
+  TORCH_CHECK(rc == 0, "frozen_bn_relu_maxpool failed (code ", rc, ")");
+  return y;
+}
+
 std::vector<at::Tensor> frozen_bn_act_backward(const at::Tensor& dy, const at::Tensor& y, const at::Tensor& scale, bool relu,
                                                bool need_dx, bool need_dres) {
   TORCH_CHECK(nhwc_dense(y) && dy.is_cuda() && dy.scalar_type() == at::kFloat && dy.sizes() == y.sizes(), "frozen_bn_act_backward: bad dy / y");
@@ -765,4 +780,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("flat_adamw", &flat_adamw);
   m.def("frozen_bn_act_forward", &frozen_bn_act_forward);
   m.def("frozen_bn_act_backward", &frozen_bn_act_backward);
+  m.def("frozen_bn_relu_maxpool", &frozen_bn_relu_maxpool);
 }

@@ -24,7 +24,6 @@ from . import ext, seeds
 
 _MIN_ROWS = 64            # from here on the column-sum kernels beat the generic reduction (single launch up to 2048 rows)
 _SPLIT_K = os.environ.get("TFB200_WGRAD_SPLITK", "0") == "1"      # opt-in: see weight_grad
-_SM_COUNT = 148
 
 
 def weight_grad(gy2: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
@@ -41,7 +40,8 @@ def weight_grad(gy2: torch.Tensor, x2: torch.Tensor) -> torch.Tensor:
     k, c_out = gy2.shape
     c_in = x2.shape[1]
     tiles = -(-c_out // 128) * -(-c_in // 128)
-    splits = min(16, max(1, (2 * _SM_COUNT) // (3 * tiles)), k // 1024)
+    sms = torch.cuda.get_device_properties(gy2.device).multi_processor_count if gy2.is_cuda else 1
+    splits = min(16, max(1, (2 * sms) // (3 * tiles)), k // 1024)
     if not _SPLIT_K or splits < 2 or not (gy2.is_contiguous() and x2.is_contiguous()):
         return gy2.t() @ x2
     slab = (k // splits) & ~7
