@@ -112,6 +112,14 @@ int msda_b200_backward_enc_tiled_f32(const float* value, const int64_t* spatial_
                                      float* grad_value, float* grad_sampling_loc, float* grad_attn_weight,
                                      int N, int S, int M, int D, int L, int Lq, int P, void* stream);
 
+/* Tile kernels with the fused prologue (proj / ref as in msda_b200_forward_fused_f32); additionally L == 4. */
+int msda_b200_forward_enc_tiled_fused_f32(const float* value, const int64_t* spatial_shapes_host, const float* proj,
+                                          const float* ref, float* output, int N, int S, int M, int D, int L, int Lq,
+                                          int P, void* stream);
+int msda_b200_backward_enc_tiled_fused_f32(const float* value, const int64_t* spatial_shapes_host, const float* proj,
+                                           const float* ref, const float* grad_output, float* grad_value,
+                                           float* grad_proj, int N, int S, int M, int D, int L, int Lq, int P, void* stream);
+
 /* ---- host-buffer entry points (H2D + kernel + D2H inside the call; synchronous) -------- */
 int msda_b200_forward_host_f32(const float* value, const int64_t* spatial_shapes,
                                const float* sampling_loc, const float* attn_weight, float* output,

@@ -604,3 +604,44 @@ def test_fused_prologue_equals_module_chain(msda, dev, D):
     torch.testing.assert_close(out, exp, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(gv, value.grad, rtol=1e-4, atol=1e-4 * float(value.grad.abs().max()))
     torch.testing.assert_close(gp, proj.grad, rtol=2e-3, atol=2e-4 * float(proj.grad.abs().max()))
+
+
+@pytest.mark.parametrize("spread", [0.6, 6.0])
+@pytest.mark.parametrize("hw", [[(37, 53), (19, 27), (10, 14), (5, 7)], [(60, 80), (30, 40), (15, 20), (8, 10)]])
+def test_fused_prologue_tile_kernels_equal_module_chain(msda, dev, hw, spread):
+    """MSDeformAttnEncFusedFunction (TMA tile kernels with softmax + location arithmetic in the tap pass) against the
+    materialising chain on the same projection: forward, grad_value and the projection gradient (offsets and logits through
+    the softmax).  spread = 6 px pushes many samples out of the staged boxes (per-sample path) and out of the image."""
+    from trackformer_b200.msda_function import MSDeformAttnEncFusedFunction, MSDeformAttnFunction
+    g = torch.Generator().manual_seed(int(spread * 10) + hw[0][0])
+    shapes = torch.as_tensor(hw, dtype=torch.long)
+    S = int((shapes[:, 0] * shapes[:, 1]).sum())
+    N, M, L, P, D = 2, 8, 4, 4, 32
+    value = torch.randn(N, S, M, D, generator=g).to(dev).requires_grad_(True)
+    proj = torch.randn(N, S, 3 * M * L * P, generator=g)
+    proj[..., :2 * M * L * P] *= spread
+    proj = proj.to(dev).requires_grad_(True)
+    refs = []
+    for (h, w) in hw:
+        ys, xs = torch.meshgrid(torch.arange(h) + 0.5, torch.arange(w) + 0.5, indexing="ij")
+        refs.append(torch.stack([xs.reshape(-1) / w, ys.reshape(-1) / h], -1))
+    ref = torch.cat(refs, 0)[None, :, None, :].expand(N, S, L, 2).contiguous().to(dev)
+    gout = torch.randn(N, S, M * D, generator=g).to(dev)
+    ts = shapes.to(dev)
+    flat_hw = [int(v) for pair in hw for v in pair]
+
+    out = MSDeformAttnEncFusedFunction.apply(value, proj, ref, flat_hw)
+    out.backward(gout)
+    gv, gp = value.grad.clone(), proj.grad.clone()
+    value.grad = proj.grad = None
+
+    n_off = 2 * M * L * P
+    offsets = proj[..., :n_off].reshape(N, S, M, L, P, 2)
+    attn = torch.softmax(proj[..., n_off:].reshape(N, S, M, L * P), -1).view(N, S, M, L, P)
+    loc = ref[:, :, None, :, None, :] + offsets / ts.float()[None, None, None, :, None, :]      # (H, W) as stored
+    exp = MSDeformAttnFunction.apply(value, ts, loc, attn, 64)
+    exp.backward(gout)
+    torch.testing.assert_close(out, exp, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(gv, value.grad, rtol=1e-4, atol=1e-4 * float(value.grad.abs().max()))
+    bad = ~torch.isclose(gp, proj.grad, rtol=2e-3, atol=2e-4 * float(proj.grad.abs().max()))
+    assert int(bad.sum()) <= 4, int(bad.sum())                # (ties on pixel boundaries, see assert_close_but_for_ties)

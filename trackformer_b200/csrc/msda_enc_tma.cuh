@@ -160,7 +160,40 @@ __device__ __forceinline__ void et_level_pass(u64 (&acc)[kEtR][et_nacc(NS)], uin
   }
 }
 
-template <int NS>
+// One sample's (normalised location, attention weight) from the module's raw projection, evaluated by a single thread
+// (far path of the fused-prologue kernels; the tap pass uses run_sample<true, 16>, one lane per slot).
+//   proj row [n, q]: [M][16][2] offsets, then [M][16] logits;  ref [n, q][L][2];  loc = ref + offset / (H, W) as stored.
+__device__ __forceinline__ void prep_sample_serial(const float* __restrict__ proj, const float* __restrict__ ref, size_t nq,
+                                                   int m, int s, int l, int M, int L, int H, int W, float& x, float& y,
+                                                   float& a) {
+  const float* prow = proj + nq * size_t(3 * M * 16);
+  const float* lg = prow + 2 * M * 16 + m * 16;
+  float v[16], mx = -INFINITY, sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(lg + i));
+    v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) mx = fmaxf(mx, v[i]);
+  float mine = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float e = expf(v[i] - mx);
+    sum += e;
+    if (i == s) mine = e;
+  }
+  a = mine / sum;
+  const float2 off = __ldg(reinterpret_cast<const float2*>(prow) + m * 16 + s);
+  const float2 r = __ldg(reinterpret_cast<const float2*>(ref) + nq * L + l);
+  x = r.x + off.x / float(H);
+  y = r.y + off.y / float(W);
+}
+
+// PREP = true (module-level fusion, ops/modules/ms_deform_attn.py:69-87 inside the kernel): `loc` is the raw output of
+// the [sampling_offsets | attention_weights] projections and `attn` the reference points; sampling locations and softmax
+// weights are computed in the tap pass and never materialised.  Needs L * P == 16.
+template <int NS, bool PREP = false>
 __global__ void __launch_bounds__(512 / NS, 2)
 msda_fwd_enc_tma_kernel(const float* __restrict__ value, const float* __restrict__ loc, const float* __restrict__ attn,
                         float* __restrict__ out, const __grid_constant__ EtGeom g, const __grid_constant__ EtMaps maps) {
@@ -213,7 +246,7 @@ msda_fwd_enc_tma_kernel(const float* __restrict__ value, const float* __restrict
     int mnx = INT_MAX, mny = INT_MAX;
     // all samples of the thread are requested before the first one is used: one HBM round trip per CTA instead of one
     // per sample (ncu, first version: 61 % of the kernel's stall samples sat on the first use of these loads)
-    float2 xy[NIT];
+    float2 xy[NIT], rf[PREP ? NIT : 1];
     float at[NIT];
     const size_t srow = size_t(M) * LPr;                      // floats of attn per query
 #pragma unroll
@@ -221,17 +254,42 @@ msda_fwd_enc_tma_kernel(const float* __restrict__ value, const float* __restrict
       const int qi = (tid >> 4) + (T / 16) * it;
       const int ix = qi & 15, iy = qi >> 4;
       const bool valid = slot_ok && (x0 + ix < Wq) && (y0 + iy < Hq);
-      const size_t sidx = (size_t(n) * Lq + qbase + iy * Wq + ix) * srow + size_t(m) * LPr + s;
-      xy[it] = valid ? __ldg(reinterpret_cast<const float2*>(loc) + sidx) : make_float2(-8.f, -8.f);
-      at[it] = valid ? __ldg(attn + sidx) : 0.f;
+      if (PREP) {
+        // raw projection: offset pair and logit of (head m, slot s); reference point of (query, level)
+        const size_t nq = size_t(n) * Lq + (valid ? qbase + iy * Wq + ix : qbase);
+        const float* prow = loc + nq * size_t(3 * M * 16);
+        xy[it] = __ldg(reinterpret_cast<const float2*>(prow) + m * 16 + s);
+        at[it] = __ldg(prow + 2 * M * 16 + m * 16 + s);
+        rf[it] = __ldg(reinterpret_cast<const float2*>(attn) + nq * L + l);
+      } else {
+        const size_t sidx = (size_t(n) * Lq + qbase + iy * Wq + ix) * srow + size_t(m) * LPr + s;
+        xy[it] = valid ? __ldg(reinterpret_cast<const float2*>(loc) + sidx) : make_float2(-8.f, -8.f);
+        at[it] = valid ? __ldg(attn + sidx) : 0.f;
+      }
     }
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
       const int qi = (tid >> 4) + (T / 16) * it;
       float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
       unsigned code = kEtNone;
-      const float a = at[it];
-      const float x = xy[it].x * float(Wl) - 0.5f, y = xy[it].y * float(Hl) - 0.5f;     // invalid queries: far outside
+      float a = at[it];
+      float lx = xy[it].x, ly = xy[it].y;
+      if (PREP) {
+        // softmax over the head's 16 logits (16 consecutive lanes), location = reference + offset / (H, W) as stored
+        float mx = a;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float e = expf(a - mx);
+        float sum = e;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        a = e / sum;
+        const int ix = qi & 15, iy = qi >> 4;
+        const bool valid = (x0 + ix < Wq) && (y0 + iy < Hq);
+        lx = valid ? rf[it].x + lx / float(Hl) : -8.f;
+        ly = valid ? rf[it].y + ly / float(Wl) : -8.f;
+      }
+      const float x = lx * float(Wl) - 0.5f, y = ly * float(Hl) - 0.5f;                 // invalid queries: far outside
       if (y > -1.f && x > -1.f && y < float(Hl) && x < float(Wl)) {
         int xb, yb;
         float wxa, wxb, wya, wyb, d0, d1;
@@ -404,9 +462,15 @@ msda_fwd_enc_tma_kernel(const float* __restrict__ value, const float* __restrict
       for (int u = 0; u < 2; ++u) {
         sl[u] = fm ? __ffs(int(fm)) - 1 : -1;
         fm &= fm - 1;                                         // (0 stays 0)
-        const size_t sidx = (qidx * M + m) * LPr + (sl[u] < 0 ? 0 : sl[u]);
-        xy[u] = __ldg(reinterpret_cast<const float2*>(loc) + sidx);
-        a[u] = sl[u] < 0 ? 0.f : __ldg(attn + sidx);
+        const int su = sl[u] < 0 ? 0 : sl[u];
+        if (PREP) {
+          prep_sample_serial(loc, attn, qidx, m, su, su >> 2, M, L, g.H[su >> 2], g.W[su >> 2], xy[u].x, xy[u].y, a[u]);
+          if (sl[u] < 0) a[u] = 0.f;
+        } else {
+          const size_t sidx = (qidx * M + m) * LPr + su;
+          xy[u] = __ldg(reinterpret_cast<const float2*>(loc) + sidx);
+          a[u] = sl[u] < 0 ? 0.f : __ldg(attn + sidx);
+        }
       }
       Tap<float> tp[2];
       float4 v[2][4];

@@ -210,6 +210,10 @@ __device__ __forceinline__ void eb_slot_pass(uint32_t sw_addr, uint32_t sa_addr,
   }
 }
 
+// PREP = true: `loc` / `attn` are the raw projection / reference points (see msda_enc_tma.cuh) and `grad_loc` receives the
+// gradient of the PROJECTION row ([M][16][2] offset gradients, then [M][16] logit gradients = softmax backward);
+// `grad_attn` is unused.
+template <bool PREP = false>
 __global__ void __launch_bounds__(kEbThreads, 2)
 msda_bwd_enc_tma_kernel(const float* __restrict__ value, const float* __restrict__ loc, const float* __restrict__ attn,
                         const float* __restrict__ grad_out, float* __restrict__ grad_value, float* __restrict__ grad_loc,
@@ -259,7 +263,7 @@ msda_bwd_enc_tma_kernel(const float* __restrict__ value, const float* __restrict
     const bool slot_ok = s < LPr;
     const int Hl = slot_ok ? g.H[l] : 2, Wl = slot_ok ? g.W[l] : 2;
     int mnx = INT_MAX, mny = INT_MAX;
-    float2 xy[NIT];
+    float2 xy[NIT], rf[PREP ? NIT : 1];
     float at[NIT];
     const size_t srow = size_t(M) * LPr;
 #pragma unroll
@@ -267,9 +271,17 @@ msda_bwd_enc_tma_kernel(const float* __restrict__ value, const float* __restrict
       const int qi = (tid >> 4) + (T / 16) * it;
       const int ix = qi & 15, iy = qi >> 4;
       const bool valid = slot_ok && (x0 + ix < Wq) && (y0 + iy < Hq);
-      const size_t sidx = (size_t(n) * Lq + qbase + iy * Wq + ix) * srow + size_t(m) * LPr + s;
-      xy[it] = valid ? __ldg(reinterpret_cast<const float2*>(loc) + sidx) : make_float2(-8.f, -8.f);
-      at[it] = valid ? __ldg(attn + sidx) : 0.f;
+      if (PREP) {
+        const size_t nq = size_t(n) * Lq + (valid ? qbase + iy * Wq + ix : qbase);
+        const float* prow = loc + nq * size_t(3 * M * 16);
+        xy[it] = __ldg(reinterpret_cast<const float2*>(prow) + m * 16 + s);
+        at[it] = __ldg(prow + 2 * M * 16 + m * 16 + s);
+        rf[it] = __ldg(reinterpret_cast<const float2*>(attn) + nq * L + l);
+      } else {
+        const size_t sidx = (size_t(n) * Lq + qbase + iy * Wq + ix) * srow + size_t(m) * LPr + s;
+        xy[it] = valid ? __ldg(reinterpret_cast<const float2*>(loc) + sidx) : make_float2(-8.f, -8.f);
+        at[it] = valid ? __ldg(attn + sidx) : 0.f;
+      }
     }
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
@@ -277,13 +289,29 @@ msda_bwd_enc_tma_kernel(const float* __restrict__ value, const float* __restrict
       float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
       float a = 0.f;
       unsigned code = kEtNone;
-      const float x = xy[it].x * float(Wl) - 0.5f, y = xy[it].y * float(Hl) - 0.5f;
+      float lx = xy[it].x, ly = xy[it].y, aw = at[it];
+      if (PREP) {
+        float mx = aw;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float e = expf(aw - mx);
+        float sum = e;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        aw = e / sum;
+        const int ix = qi & 15, iy = qi >> 4;
+        const bool valid = (x0 + ix < Wq) && (y0 + iy < Hq);
+        lx = valid ? rf[it].x + lx / float(Hl) : -8.f;
+        ly = valid ? rf[it].y + ly / float(Wl) : -8.f;
+        a = valid ? aw : 0.f;               // the softmax backward needs the weight of EVERY sample, dead ones included
+      }
+      const float x = lx * float(Wl) - 0.5f, y = ly * float(Hl) - 0.5f;
       if (y > -1.f && x > -1.f && y < float(Hl) && x < float(Wl)) {
         int xb, yb;
         float dxa, dxb, dya, dyb;
         axis_window(x, Wl, xb, w.x, w.y, dxa, dxb);
         axis_window(y, Hl, yb, w.z, w.w, dya, dyb);
-        a = at[it];
+        a = aw;
         const unsigned codes = eb_enc(dxa) | (eb_enc(dxb) << 2) | (eb_enc(dya) << 4) | (eb_enc(dyb) << 6);
         if (l < lq) {
           code = unsigned(g.start[l] + yb * Wl + xb) | (codes << 20);        // pixel of the window's first corner
@@ -446,9 +474,15 @@ msda_bwd_enc_tma_kernel(const float* __restrict__ value, const float* __restrict
         fm &= fm - 1;
         const int l = s >> 2;
         const int H = g.H[l], W = g.W[l];
-        const size_t sidx = (qidx * M + m) * LPr + s;
-        const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + sidx);
-        const float a = __ldg(attn + sidx);
+        float2 xy;
+        float a;
+        if (PREP) {
+          prep_sample_serial(loc, attn, qidx, m, s, l, M, L, H, W, xy.x, xy.y, a);
+        } else {
+          const size_t sidx = (qidx * M + m) * LPr + s;
+          xy = __ldg(reinterpret_cast<const float2*>(loc) + sidx);
+          a = __ldg(attn + sidx);
+        }
         const Tap<float> tp = make_tap<float>(xy.x, xy.y, H, W, stride);
         float s_at = 0.f, s_x = 0.f, s_y = 0.f;
         if (tp.live) {
@@ -474,7 +508,10 @@ msda_bwd_enc_tma_kernel(const float* __restrict__ value, const float* __restrict
           s_x += __shfl_xor_sync(gmask, s_x, sh);
           s_y += __shfl_xor_sync(gmask, s_y, sh);
         }
-        if (j == 0) s_w[e0 + r * kEtLP + s] = make_float4(s_at, s_x, s_y, 0.f);
+        if (j == 0) {
+          s_w[e0 + r * kEtLP + s] = make_float4(s_at, s_x, s_y, 0.f);
+          if (PREP) s_a[e0 + r * kEtLP + s] = a;             // (the plan zeroed it when it flagged the sample)
+        }
       }
     }
   }
@@ -490,8 +527,23 @@ msda_bwd_enc_tma_kernel(const float* __restrict__ value, const float* __restrict
       for (int it = 0; it < NIT; ++it) {
         const int qi = (tid >> 4) + (T / 16) * it;
         const int ix = qi & 15, iy = qi >> 4;
-        if (x0 + ix < Wq && y0 + iy < Hq) {
-          const float4 r = s_w[qi * kEtLP + s + (qi >> 3)];
+        const bool valid = x0 + ix < Wq && y0 + iy < Hq;
+        const int e = qi * kEtLP + s + (qi >> 3);
+        const float4 r = s_w[e];
+        if (PREP) {
+          // projection gradient: offsets through d(loc) / d(offset) = 1 / (H, W); logits through the softmax Jacobian
+          // a_s * (g_s - sum_j a_j g_j), the sum taken over the 16 consecutive lanes of the head
+          const float a = s_a[e];
+          float dot = a * r.x;
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+          if (valid) {
+            const int l = s >> 2;
+            float* grow = grad_loc + (size_t(n) * Lq + qbase + iy * Wq + ix) * size_t(3 * M * 16);
+            reinterpret_cast<float2*>(grow)[m * 16 + s] = make_float2(r.y / float(g.H[l]), r.z / float(g.W[l]));
+            grow[2 * M * 16 + m * 16 + s] = a * (r.x - dot);
+          }
+        } else if (valid) {
           const size_t sidx = (size_t(n) * Lq + qbase + iy * Wq + ix) * srow + size_t(m) * LPr + s;
           grad_attn[sidx] = r.x;
           *reinterpret_cast<float2*>(grad_loc + 2 * sidx) = make_float2(r.y, r.z);

@@ -748,6 +748,17 @@ static bool et_make_map(CUtensorMap* map, const float* level_base, int N, int S,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static int eb_upload_signs() {
+  static std::once_flag signs_once;
+  static cudaError_t signs_rc = cudaSuccess;
+  std::call_once(signs_once, [] {
+    EbSigns t;
+    eb_fill_signs(&t);
+    signs_rc = cudaMemcpyToSymbol(kEbSigns, &t, sizeof(t));     // (per device context: one GPU per process)
+  });
+  return int(signs_rc);
+}
+
 // Fills the tile geometry and the tensor maps of the encoder tile kernels; MSDA_E_UNSUPPORTED outside their domain.
 static int et_prepare(const float* value, const int64_t* spatial_shapes_host, int N, int S, int M, int D, int L, int Lq,
                       int P, EtGeom* g, EtMaps* maps, int64_t* grid, bool backward) {
@@ -794,12 +805,12 @@ int msda_b200_forward_enc_tiled_f32(const float* value, const int64_t* spatial_s
   int64_t grid = 0;
   if (int rc = et_prepare(value, spatial_shapes_host, N, S, M, D, L, Lq, P, &g, &maps, &grid, false)) return rc;
   if (g_fwd_variant.load(std::memory_order_relaxed) == 201) {        // A/B: four warps, four slots per warp
-    MSDA_ENSURE_SMEM(msda_fwd_enc_tma_kernel<4>, kEtSmemBytes);
-    msda_fwd_enc_tma_kernel<4><<<unsigned(grid), 128, kEtSmemBytes, cudaStream_t(stream)>>>(value, sampling_loc, attn_weight,
+    MSDA_ENSURE_SMEM((msda_fwd_enc_tma_kernel<4, false>), kEtSmemBytes);
+    msda_fwd_enc_tma_kernel<4, false><<<unsigned(grid), 128, kEtSmemBytes, cudaStream_t(stream)>>>(value, sampling_loc, attn_weight,
                                                                                            output, g, maps);
   } else {
-    MSDA_ENSURE_SMEM(msda_fwd_enc_tma_kernel<2>, kEtSmemBytes);
-    msda_fwd_enc_tma_kernel<2><<<unsigned(grid), kEtThreads, kEtSmemBytes, cudaStream_t(stream)>>>(value, sampling_loc,
+    MSDA_ENSURE_SMEM((msda_fwd_enc_tma_kernel<2, false>), kEtSmemBytes);
+    msda_fwd_enc_tma_kernel<2, false><<<unsigned(grid), kEtThreads, kEtSmemBytes, cudaStream_t(stream)>>>(value, sampling_loc,
                                                                                                   attn_weight, output, g, maps);
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -825,20 +836,53 @@ int msda_b200_backward_enc_tiled_f32(const float* value, const int64_t* spatial_
   cudaStream_t st = cudaStream_t(stream);
   cudaError_t e = cudaMemsetAsync(grad_value, 0, sizeof(float) * size_t(N) * S * M * D, st);
   if (e != cudaSuccess) return int(e);
-  {
-    static std::once_flag signs_once;
-    static cudaError_t signs_rc = cudaSuccess;
-    std::call_once(signs_once, [] {
-      EbSigns t;
-      eb_fill_signs(&t);
-      signs_rc = cudaMemcpyToSymbol(kEbSigns, &t, sizeof(t));     // (per device context: one GPU per process)
-    });
-    if (signs_rc != cudaSuccess) return int(signs_rc);
-  }
-  MSDA_ENSURE_SMEM(msda_bwd_enc_tma_kernel, kEbSmemBytes);
-  msda_bwd_enc_tma_kernel<<<unsigned(grid), kEbThreads, kEbSmemBytes, st>>>(value, sampling_loc, attn_weight, grad_output,
-                                                                           grad_value, grad_sampling_loc, grad_attn_weight, g,
-                                                                           maps);
+  if (int rc = eb_upload_signs()) return rc;
+  MSDA_ENSURE_SMEM(msda_bwd_enc_tma_kernel<false>, kEbSmemBytes);
+  msda_bwd_enc_tma_kernel<false><<<unsigned(grid), kEbThreads, kEbSmemBytes, st>>>(
+      value, sampling_loc, attn_weight, grad_output, grad_value, grad_sampling_loc, grad_attn_weight, g, maps);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+
+// Encoder tile kernels with the module's location / softmax arithmetic inside (ops/modules/ms_deform_attn.py:69-87):
+// proj [N][Lq][3*M*16] = [offsets | logits], ref [N][Lq][L][2].  Domain: the tile kernels' (fp32, D = 32, Lq == S) and L == 4.
+int msda_b200_forward_enc_tiled_fused_f32(const float* value, const int64_t* spatial_shapes_host, const float* proj,
+                                          const float* ref, float* output, int N, int S, int M, int D, int L, int Lq,
+                                          int P, void* stream) {
+  const Dims d{N, S, M, D, L, Lq, P};
+  if (int rc = check_dims(d)) return rc;
+  if (!value || !spatial_shapes_host || !proj || !ref || !output) return MSDA_E_NULLPTR;
+  if (L != 4 || !aligned16(proj) || !aligned16(ref) || !aligned16(output)) return MSDA_E_UNSUPPORTED;
+  EtGeom g;
+  EtMaps maps;
+  int64_t grid = 0;
+  if (int rc = et_prepare(value, spatial_shapes_host, N, S, M, D, L, Lq, P, &g, &maps, &grid, false)) return rc;
+  MSDA_ENSURE_SMEM((msda_fwd_enc_tma_kernel<2, true>), kEtSmemBytes);
+  msda_fwd_enc_tma_kernel<2, true><<<unsigned(grid), kEtThreads, kEtSmemBytes, cudaStream_t(stream)>>>(value, proj, ref, output,
+                                                                                                    g, maps);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return int(cudaGetLastError());
+}
+
+int msda_b200_backward_enc_tiled_fused_f32(const float* value, const int64_t* spatial_shapes_host, const float* proj,
+                                           const float* ref, const float* grad_output, float* grad_value, float* grad_proj,
+                                           int N, int S, int M, int D, int L, int Lq, int P, void* stream) {
+  const Dims d{N, S, M, D, L, Lq, P};
+  if (int rc = check_dims(d)) return rc;
+  if (!value || !spatial_shapes_host || !proj || !ref || !grad_output || !grad_value || !grad_proj) return MSDA_E_NULLPTR;
+  if (L != 4 || !aligned16(proj) || !aligned16(ref) || !aligned16(grad_output) || !aligned16(grad_value) || !aligned16(grad_proj))
+    return MSDA_E_UNSUPPORTED;
+  EtGeom g;
+  EtMaps maps;
+  int64_t grid = 0;
+  if (int rc = et_prepare(value, spatial_shapes_host, N, S, M, D, L, Lq, P, &g, &maps, &grid, true)) return rc;
+  cudaStream_t st = cudaStream_t(stream);
+  cudaError_t e = cudaMemsetAsync(grad_value, 0, sizeof(float) * size_t(N) * S * M * D, st);
+  if (e != cudaSuccess) return int(e);
+  if (int rc = eb_upload_signs()) return rc;
+  MSDA_ENSURE_SMEM(msda_bwd_enc_tma_kernel<true>, kEbSmemBytes);
+  msda_bwd_enc_tma_kernel<true><<<unsigned(grid), kEbThreads, kEbSmemBytes, st>>>(value, proj, ref, grad_output, grad_value,
+                                                                                 grad_proj, nullptr, g, maps);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return int(cudaGetLastError());
 }

@@ -202,6 +202,42 @@ std::vector<at::Tensor> ms_deform_attn_backward_fused(const at::Tensor& value, c
   return {gv, gp};
 }
 
+// Encoder tile kernels with the fused prologue: proj [N, Lq, 3*M*16], ref [N, Lq, 4, 2], hw = host level sizes.
+// Raise (no fallback: the caller chose this path) outside the domain.
+at::Tensor ms_deform_attn_forward_enc_fused(const at::Tensor& value, const at::Tensor& proj, const at::Tensor& ref,
+                                            const std::vector<int64_t>& hw) {
+  TORCH_CHECK(value.is_cuda() && proj.is_cuda() && ref.is_cuda(), "Not implemented on the CPU");
+  TORCH_CHECK(value.scalar_type() == at::kFloat && proj.scalar_type() == at::kFloat && ref.scalar_type() == at::kFloat &&
+              value.dim() == 4 && proj.dim() == 3 && ref.dim() == 4 && ref.size(3) == 2 && hw.size() == 8,
+              "ms_deform_attn_forward_enc_fused: dtypes / ranks (four levels)");
+  const at::Tensor v = value.contiguous(), pr = proj.contiguous(), rf = ref.contiguous();
+  const int64_t N = v.size(0), S = v.size(1), M = v.size(2), D = v.size(3), L = 4, Lq = pr.size(1), P = 4;
+  TORCH_CHECK(pr.size(0) == N && pr.size(2) == 3 * M * L * P && rf.size(0) == N && rf.size(1) == Lq && rf.size(2) == L,
+              "ms_deform_attn_forward_enc_fused: shapes");
+  const c10::cuda::CUDAGuard guard(value.device());
+  at::Tensor out = at::empty({N, Lq, M * D}, v.options());
+  const int rc = msda_b200_forward_enc_tiled_fused_f32(v.data_ptr<float>(), hw.data(), pr.data_ptr<float>(), rf.data_ptr<float>(),
+                                                       out.data_ptr<float>(), int(N), int(S), int(M), int(D), int(L), int(Lq),
+                                                       int(P), c10::cuda::getCurrentCUDAStream().stream());
+  raise_on_error(rc, "ms_deform_attn_forward_enc_fused");
+  return out;
+}
+
+std::vector<at::Tensor> ms_deform_attn_backward_enc_fused(const at::Tensor& value, const at::Tensor& proj, const at::Tensor& ref,
+                                                          const at::Tensor& grad_output, const std::vector<int64_t>& hw) {
+  const at::Tensor v = value.contiguous(), pr = proj.contiguous(), rf = ref.contiguous(), go = grad_output.contiguous();
+  const int64_t N = v.size(0), S = v.size(1), M = v.size(2), D = v.size(3), L = 4, Lq = pr.size(1), P = 4;
+  TORCH_CHECK(hw.size() == 8 && go.numel() == N * Lq * M * D, "ms_deform_attn_backward_enc_fused: shapes");
+  const c10::cuda::CUDAGuard guard(value.device());
+  at::Tensor gv = at::empty_like(v), gp = at::empty_like(pr);
+  const int rc = msda_b200_backward_enc_tiled_fused_f32(v.data_ptr<float>(), hw.data(), pr.data_ptr<float>(), rf.data_ptr<float>(),
+                                                        go.data_ptr<float>(), gv.data_ptr<float>(), gp.data_ptr<float>(), int(N),
+                                                        int(S), int(M), int(D), int(L), int(Lq), int(P),
+                                                        c10::cuda::getCurrentCUDAStream().stream());
+  raise_on_error(rc, "ms_deform_attn_backward_enc_fused");
+  return {gv, gp};
+}
+
 static at::Tensor forward_enc_impl(const at::Tensor& value, const at::Tensor& spatial_shapes,
                                    const at::Tensor& sampling_loc, const at::Tensor& attn_weight,
                                    const std::vector<int64_t>& hw, const int64_t im2col_step, bool strict);
@@ -753,6 +789,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("ms_deform_attn_forward_enc_strict", &ms_deform_attn_forward_enc_strict);
   m.def("ms_deform_attn_backward_enc", &ms_deform_attn_backward_enc);
   m.def("ms_deform_attn_backward_enc_strict", &ms_deform_attn_backward_enc_strict);
+  m.def("ms_deform_attn_forward_enc_fused", &ms_deform_attn_forward_enc_fused);
+  m.def("ms_deform_attn_backward_enc_fused", &ms_deform_attn_backward_enc_fused);
   m.def("ms_deform_attn_forward_fused", &ms_deform_attn_forward_fused);
   m.def("ms_deform_attn_backward_fused", &ms_deform_attn_backward_fused);
   m.def("add_dropout_layernorm_forward", &add_dropout_layernorm_forward);

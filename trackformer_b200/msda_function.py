@@ -169,6 +169,61 @@ class MSDeformAttnEncFunction(Function):
         return _backward(ctx, grad_output, ctx.hw if tile else None)
 
 
+class MSDeformAttnEncFusedFunction(Function):
+    """Encoder tile kernels with the module's location / softmax arithmetic inside (sampling locations and
+    attention weights are never materialised): ``proj`` is the raw output of the [sampling_offsets | attention_weights]
+    projections, ``reference_points`` [N, Lq, 4, 2], ``hw`` the host level sizes.  Gradients for ``value`` and ``proj``.
+    bench.py's roofline leg keeps the UNFUSED algorithmic bytes as the yardstick for these launches."""
+
+    @staticmethod
+    def forward(ctx, value, proj, reference_points, hw):
+        msda = ext.load()
+        ctx.hw = list(hw)
+        sink = _TIMING_SINK
+        if sink is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        out = msda.ms_deform_attn_forward_enc_fused(value, proj, reference_points, ctx.hw)
+        if sink is not None:
+            e1.record()
+            n, s_, m, d = value.shape
+            sink.append(("fwd", (n, s_, m, d, 4, proj.shape[1], 4), e0, e1))
+        ctx.save_for_backward(value, proj, reference_points)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, proj, ref = ctx.saved_tensors
+        sink = _TIMING_SINK
+        if sink is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        gv, gp = ext.load().ms_deform_attn_backward_enc_fused(value, proj, ref, grad_output.contiguous(), ctx.hw)
+        if sink is not None:
+            e1.record()
+            n, s_, m, d = value.shape
+            sink.append(("bwd", (n, s_, m, d, 4, proj.shape[1], 4), e0, e1))
+        return gv, gp, None, None
+
+
+_ENC_FUSED_CHOICE = {}
+_TILED_ENC_FUSED = _os.environ.get("TFB200_TILED_ENC_FUSED", "auto")     # "auto" | "1" | "0"
+
+
+def encoder_fused_choice(key, time_fused, time_unfused) -> bool:
+    """One-time decision per geometry between the fused-prologue tile kernels and the materialising path (sampling-prep
+    kernel + the autotuned op); both callables run the complete forward alternative once and are timed on the data at hand."""
+    if _TILED_ENC_FUSED in ("0", "1"):
+        return _TILED_ENC_FUSED == "1"
+    choice = _ENC_FUSED_CHOICE.get(key)
+    if choice is None:
+        if torch.cuda.is_current_stream_capturing():
+            return False
+        choice = _ENC_FUSED_CHOICE[key] = _time_us(time_fused) < 0.97 * _time_us(time_unfused)
+    return choice
+
+
 def ms_deform_attn(value: torch.Tensor, spatial_shapes: torch.Tensor, sampling_locations: torch.Tensor,
                    attention_weights: torch.Tensor, im2col_step: int = 64) -> torch.Tensor:
     """Functional form: ``[N,S,M,D] x [L,2] x [N,Lq,M,L,P,2] x [N,Lq,M,L,P] -> [N,Lq,M*D]``."""

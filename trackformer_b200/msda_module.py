@@ -21,7 +21,8 @@ import torch.nn.functional as F
 from torch import nn
 
 from .fused_linear import linear as fused_linear
-from .msda_function import MSDeformAttnEncFunction, MSDeformAttnFunction, MSDeformAttnFusedFunction
+from .msda_function import (MSDeformAttnEncFunction, MSDeformAttnEncFusedFunction, MSDeformAttnFunction,
+                            MSDeformAttnFusedFunction, encoder_fused_choice)
 
 # fold sampling_prep into the MSDeformAttn kernels (csrc/msda_run.cuh PREP variants); off until validated on a B200
 _FUSED_PREP = os.environ.get("TFB200_FUSED_PREP", "0") != "0"
@@ -143,6 +144,26 @@ class MSDeformAttn(nn.Module):
             # and attention weights never touch HBM (ms_deform_attn.py:69-87 as one launch per direction)
             out = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, proj, reference_points, points)
             return fused_linear(out, self.output_proj.weight, self.output_proj.bias)
+        if (hw is not None and len_q == len_in and proj.is_cuda and proj.dtype == torch.float32 and query_attn_mask is None
+                and not reference_points.requires_grad and reference_points.shape[-1] == 2 and levels == 4 and points == 4
+                and d_head == 32):
+            # encoder call: the TMA tile kernels can evaluate softmax + locations in their tap pass; taken when that beats
+            # "sampling-prep kernel + op" on this geometry (timed once on the first eager call)
+            flat_hw = [int(v) for pair in hw for v in pair]
+            key = (tuple(value.shape), tuple(flat_hw), value.device.index)
+
+            def unfused():
+                with torch.no_grad():
+                    lc, at = _SamplingPrep.apply(proj, reference_points, self._float_shapes(input_spatial_shapes, proj),
+                                                 heads, levels, points)
+                    return MSDeformAttnEncFunction.apply(value, input_spatial_shapes, lc, at, self.im2col_step)
+
+            def fused():
+                with torch.no_grad():
+                    return MSDeformAttnEncFusedFunction.apply(value, proj, reference_points, flat_hw)
+            if encoder_fused_choice(key, fused, unfused):
+                out = MSDeformAttnEncFusedFunction.apply(value, proj, reference_points, flat_hw)
+                return fused_linear(out, self.output_proj.weight, self.output_proj.bias)
         fusable = (proj.is_cuda and proj.dtype == torch.float32 and query_attn_mask is None
                    and not reference_points.requires_grad and reference_points.shape[-1] in (2, 4)
                    and lp in (4, 8, 16, 32) and (heads * lp) % 32 == 0)
