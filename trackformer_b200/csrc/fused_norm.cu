@@ -282,28 +282,30 @@ colsum_kernel(const float* __restrict__ x, float* __restrict__ partial, int64_t 
 
 // Small matrices (the decoder side: a few hundred rows): ONE launch, CTA = 32 columns x 8 warps striding the rows,
 // fixed summation order.  (The generic ATen reduction needs 7-16 us for a [300, 256] column sum, ~50 of them per step.)
-__global__ void __launch_bounds__(256)
+constexpr int kSmallWarps = 32;
+__global__ void __launch_bounds__(kSmallWarps * 32)
 colsum_small_kernel(const float* __restrict__ x, float* __restrict__ out, int rows, int C) {
-  __shared__ float red[8][32];
+  // (first version: 8 warps per CTA, 10.7 us per [300, 256] call under ncu -- latency bound; 32 warps x 4 loads in flight)
+  __shared__ float red[kSmallWarps][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (c < C) {
     int r = w;
-    for (; r + 24 < rows; r += 32) {                  // four independent loads in flight per lane
+    for (; r + 3 * kSmallWarps < rows; r += 4 * kSmallWarps) {
       a0 += __ldg(x + size_t(r) * C + c);
-      a1 += __ldg(x + size_t(r + 8) * C + c);
-      a2 += __ldg(x + size_t(r + 16) * C + c);
-      a3 += __ldg(x + size_t(r + 24) * C + c);
+      a1 += __ldg(x + size_t(r + kSmallWarps) * C + c);
+      a2 += __ldg(x + size_t(r + 2 * kSmallWarps) * C + c);
+      a3 += __ldg(x + size_t(r + 3 * kSmallWarps) * C + c);
     }
-    for (; r < rows; r += 8) a0 += __ldg(x + size_t(r) * C + c);
+    for (; r < rows; r += kSmallWarps) a0 += __ldg(x + size_t(r) * C + c);
   }
   red[w][lane] = (a0 + a1) + (a2 + a3);
   __syncthreads();
   if (w == 0 && c < C) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    for (int k = 0; k < kSmallWarps; ++k) t += red[k][lane];
     out[c] = t;
   }
 }
@@ -456,7 +458,7 @@ int tfb200_colsum_f32(const float* x, float* out, float* partial_ws, int64_t row
     return int(cudaGetLastError());
   }
   if (rows <= 2048) {
-    colsum_small_kernel<<<(C + 31) / 32, 256, 0, st>>>(x, out, int(rows), C);
+    colsum_small_kernel<<<(C + 31) / 32, kSmallWarps * 32, 0, st>>>(x, out, int(rows), C);
     msda_b200_count_launches(1);
     return int(cudaGetLastError());
   }
