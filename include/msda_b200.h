@@ -106,8 +106,10 @@ int msda_b200_forward_enc_tiled_f32(const float* value, const int64_t* spatial_s
                                     int N, int S, int M, int D, int L, int Lq, int P, void* stream);
 /* Backward twin (same contract as msda_b200_backward_f32: grad_value is zero-filled and accumulated, the other two are
  * overwritten; replaces ms_deform_attn_cuda_backward, ms_deform_attn_cuda.cu:89-168, for encoder call sites).  Domain as
- * the forward, plus H, W <= 4095 and S < 2^20.                                                                   */
+ * the forward, plus H, W <= 4095 and S < 2^20.  With the device copy of the level sizes given, the queries of levels >= 1
+ * (whose samples on finer levels cannot be staged) are served by the 8-lane-group kernel in a second launch.            */
 int msda_b200_backward_enc_tiled_f32(const float* value, const int64_t* spatial_shapes_host,
+                                     const int64_t* spatial_shapes_dev /* device copy, or NULL */,
                                      const float* sampling_loc, const float* attn_weight, const float* grad_output,
                                      float* grad_value, float* grad_sampling_loc, float* grad_attn_weight,
                                      int N, int S, int M, int D, int L, int Lq, int P, void* stream);

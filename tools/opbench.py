@@ -150,8 +150,8 @@ def main():
                     else:
                         fn = lambda: msda.ms_deform_attn_forward(value, shapes, loc, attn, 64)
                 else:
-                    msda.set_variant(0, 0 if v == -1 else v)
-                    if v == -1:      # TMA-staged backward tile kernel of the encoder
+                    msda.set_variant(0, 0 if v == -1 else (203 if v == -3 else v))
+                    if v in (-1, -3):      # TMA-staged backward tile kernel of the encoder (-3: coarse-level queries on the 8-lane-group kernel)
                         if dims["Lq"] != dims["S"]:
                             continue
                         flat_hw = [int(x) for x in shapes.cpu().flatten().tolist()]

@@ -52,6 +52,7 @@ constexpr size_t kEtSmemBytes = 128 + size_t(kEtBuf0Rows + kEtBuf1Rows) * 128 + 
 
 struct EtGeom {
   int L, S, M, Lq;
+  int tiles_used;                                             // tiles the grid covers (all, or only those of query level 0)
   int H[kEtMaxL], W[kEtMaxL], start[kEtMaxL];
   int tiles_x[kEtMaxL], tile_begin[kEtMaxL + 1];
 };
@@ -217,7 +218,7 @@ msda_fwd_enc_tma_kernel(const float* __restrict__ value, const float* __restrict
   const int stride = M * D;
 
   // ---- which head / tile / image
-  const int tiles = g.tile_begin[L];
+  const int tiles = g.tiles_used;
   const int m = blockIdx.x % M;
   const int t = tiles - 1 - int((blockIdx.x / M) % tiles);     // coarse query levels (the longest CTAs) first
   const int n = blockIdx.x / (M * tiles);

@@ -236,7 +236,7 @@ msda_bwd_enc_tma_kernel(const float* __restrict__ value, const float* __restrict
   const int L = g.L, M = g.M, Lq = g.Lq, LPr = L * kEtP;
   const int stride = M * D;
 
-  const int tiles = g.tile_begin[L];
+  const int tiles = g.tiles_used;
   const int m = blockIdx.x % M;
   const int t = tiles - 1 - int((blockIdx.x / M) % tiles);
   const int n = blockIdx.x / (M * tiles);

@@ -639,7 +639,10 @@ int msda_b200_l1_gather_probe(const float* table, float* sink, int64_t rows, int
   return int(cudaGetLastError());
 }
 
-int msda_b200_variant_allows_tiles(void) { const int v = g_fwd_variant.load(); return (v == 0 || v >= 200) ? 1 : 0; }
+int msda_b200_variant_allows_tiles(void) {
+  const int v = g_fwd_variant.load(), b = g_bwd_variant.load();
+  return ((v == 0 || v >= 200) && (b == 0 || b >= 200)) ? 1 : 0;
+}
 
 int msda_b200_forward_f32(const float* value, const int64_t* spatial_shapes, const float* sampling_loc,
                           const float* attn_weight, float* output, int N, int S, int M, int D, int L,
@@ -782,6 +785,7 @@ static int et_prepare(const float* value, const int64_t* spatial_shapes_host, in
     acc += h * w;
   }
   for (int l = L; l <= kEtMaxL; ++l) g->tile_begin[l] = tiles;
+  g->tiles_used = tiles;
   if (acc != S) return MSDA_E_UNSUPPORTED;
   *grid = int64_t(tiles) * M * N;
   if (*grid > INT32_MAX) return MSDA_E_UNSUPPORTED;
@@ -817,10 +821,45 @@ int msda_b200_forward_enc_tiled_f32(const float* value, const int64_t* spatial_s
   return int(cudaGetLastError());
 }
 
-int msda_b200_backward_enc_tiled_f32(const float* value, const int64_t* spatial_shapes_host, const float* sampling_loc,
-                                     const float* attn_weight, const float* grad_output, float* grad_value,
-                                     float* grad_sampling_loc, float* grad_attn_weight, int N, int S, int M, int D, int L,
-                                     int Lq, int P, void* stream) {
+// 8-lane-group backward on the queries [q_first, Lq) of every image (no zero-fill: the caller did it)
+static int bwd_d32_query_range(const float* value, const int64_t* shapes_dev, const float* loc, const float* attn,
+                               const float* gout, float* gval, float* gloc, float* gattn, const Dims& d, int q_first,
+                               cudaStream_t st) {
+  const int LP = d.L * d.P;
+  const int nq = d.Lq - q_first;
+  if (nq <= 0) return 0;
+  const size_t smem = bwd_d32_smem_bytes(LP);
+  for (int n = 0; n < d.N; ++n) {
+    const size_t qo = size_t(n) * d.Lq + q_first;
+    const float* v = value + size_t(n) * d.S * d.M * d.D;
+    float* gv = gval + size_t(n) * d.S * d.M * d.D;
+    const float* lc = loc + qo * d.M * LP * 2;
+    const float* at = attn + qo * d.M * LP;
+    const float* go = gout + qo * d.M * d.D;
+    float* gl = gloc + qo * d.M * LP * 2;
+    float* ga = gattn + qo * d.M * LP;
+    const int64_t groups = int64_t(nq) * d.M;
+    const int64_t ctas = (groups + kGroupsPerCta - 1) / kGroupsPerCta;
+    const int iters = pick_iters(ctas);
+    const unsigned grid = unsigned((ctas + iters - 1) / iters);
+    if (d.M == 8) {
+      MSDA_ENSURE_SMEM((msda_bwd_d32_kernel<256, 4>), smem);
+      msda_bwd_d32_kernel<256, 4><<<grid, kD32Threads, smem, st>>>(v, shapes_dev, lc, at, go, gv, gl, ga, d.S, d.M, d.L, nq, d.P,
+                                                                   uint32_t(groups), iters);
+    } else {
+      MSDA_ENSURE_SMEM((msda_bwd_d32_kernel<0>), smem);
+      msda_bwd_d32_kernel<0><<<grid, kD32Threads, smem, st>>>(v, shapes_dev, lc, at, go, gv, gl, ga, d.S, d.M, d.L, nq, d.P,
+                                                              uint32_t(groups), iters);
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  return int(cudaGetLastError());
+}
+
+int msda_b200_backward_enc_tiled_f32(const float* value, const int64_t* spatial_shapes_host,
+                                     const int64_t* spatial_shapes_dev, const float* sampling_loc, const float* attn_weight,
+                                     const float* grad_output, float* grad_value, float* grad_sampling_loc,
+                                     float* grad_attn_weight, int N, int S, int M, int D, int L, int Lq, int P, void* stream) {
   const Dims d{N, S, M, D, L, Lq, P};
   if (int rc = check_dims(d)) return rc;
   if (!value || !spatial_shapes_host || !sampling_loc || !attn_weight || !grad_output || !grad_value || !grad_sampling_loc ||
@@ -837,11 +876,26 @@ int msda_b200_backward_enc_tiled_f32(const float* value, const int64_t* spatial_
   cudaError_t e = cudaMemsetAsync(grad_value, 0, sizeof(float) * size_t(N) * S * M * D, st);
   if (e != cudaSuccess) return int(e);
   if (int rc = eb_upload_signs()) return rc;
+  // Queries of the coarser levels (25 % of a C2 call) sample the finer levels with a footprint of 2-8x the tile: the tile
+  // kernel walks those levels from global memory, one L2 round trip per step, and its slowest CTAs are exactly these
+  // (16 % of the kernel's time for 8 % of the samples, ncu).  Experiment: with the device copy of the level sizes at hand
+  // they can go to the 8-lane-group kernel instead while the tile kernel keeps the level-0 tiles.
+  // Measured on B200 (C2 call): 220 us with the split against 216 us without -- the 8-lane-group kernel needs as long for
+  // that quarter of the queries as the tile kernel's slow CTAs, so the split is OFF unless asked for (variant 203).
+  const bool split = spatial_shapes_dev != nullptr && L > 1 && g_bwd_variant.load(std::memory_order_relaxed) == 203;
+  if (split) {
+    g.tiles_used = g.tile_begin[1];
+    grid = int64_t(g.tiles_used) * M * N;
+  }
   MSDA_ENSURE_SMEM(msda_bwd_enc_tma_kernel<false>, kEbSmemBytes);
   msda_bwd_enc_tma_kernel<false><<<unsigned(grid), kEbThreads, kEbSmemBytes, st>>>(
       value, sampling_loc, attn_weight, grad_output, grad_value, grad_sampling_loc, grad_attn_weight, g, maps);
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  return int(cudaGetLastError());
+  if (int rc = int(cudaGetLastError())) return rc;
+  if (split)
+    return bwd_d32_query_range(value, spatial_shapes_dev, sampling_loc, attn_weight, grad_output, grad_value, grad_sampling_loc,
+                               grad_attn_weight, d, g.start[1], st);
+  return 0;
 }
 
 // Encoder tile kernels with the module's location / softmax arithmetic inside (ops/modules/ms_deform_attn.py:69-87):

@@ -144,8 +144,10 @@ static std::vector<at::Tensor> backward_enc_impl(const at::Tensor& value, const 
     const c10::cuda::CUDAGuard guard(value.device());
     const at::Tensor loc = sampling_loc.contiguous(), attn = attn_weight.contiguous(), gout = grad_output.contiguous();
     at::Tensor grad_value = at::empty_like(value), grad_loc = at::empty_like(loc), grad_attn = at::empty_like(attn);
+    const at::Tensor shapes = spatial_shapes.contiguous();
     const int rc = msda_b200_backward_enc_tiled_f32(
-        value.data_ptr<float>(), hw.data(), loc.data_ptr<float>(), attn.data_ptr<float>(), gout.data_ptr<float>(),
+        value.data_ptr<float>(), hw.data(), shapes.data_ptr<int64_t>(), loc.data_ptr<float>(), attn.data_ptr<float>(),
+        gout.data_ptr<float>(),
         grad_value.data_ptr<float>(), grad_loc.data_ptr<float>(), grad_attn.data_ptr<float>(), g.N, g.S, g.M, g.D, g.L, g.Lq,
         g.P, c10::cuda::getCurrentCUDAStream().stream());
     if (rc == 0) return {grad_value, grad_loc, grad_attn};
