@@ -294,7 +294,9 @@ static Family pick_family(int variant, int64_t groups, const Dims& d) {
   // ~0.3x but serialise one window load per group and need 41-49 KB of shared memory per CTA (little L1 left), and end
   // up latency bound -- C2 encoder forward 121 us (run8) / 96 us (run4) / 106 us (run2) against 102 us for the
   // 8-lane-group kernels, backward 286 / 228 vs 235 us.  They stay selectable (variants 100, 101, 120, 121).
-  (void)run_ok;
+  // The multi-frame geometry (D = 36, C5 encoder call) is the exception: R = 4 runs take 256 us forward / 669 us backward
+  // against 275 us (nine-lane kernel) / 841 us (generic backward) -- profiles/r2_opbench_c5.json.
+  if (run_ok && d.D == 36 && d.Lq >= 2048) return Family::kRun4;
   return Family::kD32;
 }
 
