@@ -222,6 +222,122 @@ def cpu_reference_arm(steps, warmup, batch):
     return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads()
 
 
+# --------------------------------------------------------------------------------------------- configs[4]
+def c5_arm(args, rank, local_rank, world):
+    """BASELINE configs[4]: MOT20-crowd shape 3x1080x1920, multi-frame attention (hidden 288, 8 decoder levels), 500 object
+    queries + track queries carried over from the previous frame; one train-mode step = previous-frame forward (no grad,
+    engine.py / detr_tracking.py:219-262) + matching + track-query injection + current-frame forward + SetCriterion +
+    backward + [DDP-style gradient all-reduce] + clip + AdamW.  Eager launch path: the injection bookkeeping draws from the
+    host RNG and reads the matching back, exactly like the reference, so this workload is not graph-captured."""
+    import datetime
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
+    tf32 = not args.no_tf32
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    torch.backends.cudnn.allow_tf32 = tf32
+    torch.backends.cudnn.benchmark = True
+    from trackformer_b200 import ext
+    from trackformer_b200.model_factory import build_model, default_args
+    msda = ext.load()
+    torch.manual_seed(0)
+    model, criterion, _ = build_model(default_args(tracking=True, multi_frame=True, device=str(dev), num_queries=500))
+    model.to(dev).train()
+    criterion.to(dev).train()
+    h5, w5, n_gt = 1080, 1920, 60
+    bpg = args.batch_per_gpu
+    g = torch.Generator().manual_seed(1 + rank)
+    host = torch.randn(bpg, 2, 3, h5, w5, generator=g).pin_memory()          # (current, previous) frame pairs
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=2e-4, weight_decay=1e-4, fused=True)
+    flat = torch.zeros(sum(p.numel() for p in params), device=dev) if world > 1 else None
+    wd = criterion.weight_dict
+
+    def targets_for(frames):
+        gg = torch.Generator().manual_seed(7 + rank)
+        out = []
+        for b in range(bpg):
+            cxcy = torch.rand(n_gt, 2, generator=gg) * 0.8 + 0.1
+            wh = torch.rand(n_gt, 2, generator=gg) * 0.08 + 0.02
+            boxes = torch.cat([cxcy, wh], 1).to(dev)
+            t = {"boxes": boxes, "labels": torch.zeros(n_gt, dtype=torch.int64, device=dev),
+                 "track_ids": torch.arange(n_gt, device=dev), "image_id": torch.tensor([b], device=dev)}
+            pt = {k: v.clone() for k, v in t.items()}
+            pt["boxes"] = (pt["boxes"] + 0.005).clamp(0.02, 0.98)
+            t["prev_target"] = pt
+            t["prev_image"] = frames[b, 1]
+            out.append(t)
+        return out
+
+    def step(frames):
+        tg = targets_for(frames)
+        out, tg_out, *_ = model(frames[:, 0], tg)
+        losses = criterion(out, tg_out)
+        loss = sum(losses[k] * wd[k] for k in losses if k in wd)
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:                                                          # flat all-reduce (DDP's job in the reference)
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in params]
+            torch._foreach_copy_(list(flat.split([p.numel() for p in params])), [x.reshape(-1) for x in grads])
+            dist.all_reduce(flat)
+            flat.div_(world)
+            for p, chunk in zip(params, flat.split([p.numel() for p in params])):
+                p.grad = chunk.view_as(p)
+        torch.nn.utils.clip_grad_norm_(params, 0.1)
+        opt.step()
+        return loss.detach()
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize(dev)
+
+    dev_frames = host.to(dev)
+    for _ in range(max(args.warmup, 3)):
+        step(dev_frames)
+
+    def timed(fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = msda.launch_count()
+    ms_total = timed(lambda: step(dev_frames))
+    launches = msda.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = timed(lambda: float(step(host.to(dev, non_blocking=True)).item()))
+    if rank == 0:
+        line = {"metric": "frames/sec TrackFormer multi-frame train step 1080x1920 (BASELINE configs[4])",
+                "value": bpg * world * args.steps / (ms_total / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "tf32+f32" if tf32 else "f32", "data": "synthetic",
+                "config": {"workload": f"TrackFormer multi-frame (hidden 288, D = 36, 8 decoder levels), {bpg}x3x{h5}x{w5} per GPU, "
+                                       f"500 object queries + track queries of the previous frame, {n_gt} boxes per frame "
+                                       "(BASELINE configs[4])", "global_batch": bpg * world, "parallelism": f"dp{world}",
+                           "execution": "eager (host-RNG track-query injection like the reference); previous-frame forward + "
+                                        "current-frame forward + SetCriterion + backward + clip + torch AdamW(fused)",
+                           "l2": "one step streams > 2 GB of activations"},
+                "e2e": {"value": bpg * world * args.steps / (ms_e2e / 1e3), "unit": "frames/s",
+                        "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -236,6 +352,10 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="eager step instead of CUDA-graph replay")
     ap.add_argument("--two-graphs", action="store_true",
                     help="forward graph + eager loss + backward graph instead of the single full-step graph")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2 = BASELINE configs[1] (default; configs[3] with --batch-per-gpu 2 --gpus 8); c5 = configs[4]: "
+                         "multi-frame TrackFormer train step at 3x1080x1920, 500 object queries + track queries from the "
+                         "previous frame (eager: the track-query injection draws from the host RNG, like the reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
     args = ap.parse_args()
@@ -270,6 +390,8 @@ def main():
 
     # ------------------------------------------------------------------ B200 arm
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback for the product path)"
+    if args.workload == "c5":
+        return c5_arm(args, rank, local_rank, world)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
