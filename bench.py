@@ -141,33 +141,50 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.idx, self.rows, self.proc = gpu_index, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Launch nvidia-smi (25 ms period).  Call it BEFORE the warm-up: the tool needs a few hundred ms to come up, and
+        the default timed region (20 steps) is only ~0.25 s long; `mark_begin` / `mark_end` bracket the timed region."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "25", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)                                   # let the sample that covers the end of the region arrive
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = self.t1 if self.t1 is not None else float("inf")
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.05]
+        window = "timed region"
+        if len(rows) < 2:                                  # very short region: take the samples around it as well
+            rows = [r for t, r in self.rows if t0 - 0.3 <= t <= t1 + 0.3]
+            window = "timed region +-0.3 s"
+        sm = [float(r[1]) for r in rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 8:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------------------------- CPU arm
@@ -294,6 +311,9 @@ def c5_arm(args, rank, local_rank, world):
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize(dev)
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     dev_frames = host.to(dev)
     for _ in range(max(args.warmup, 3)):
         step(dev_frames)
@@ -311,12 +331,13 @@ def c5_arm(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.mark_begin()
     l0 = msda.launch_count()
     ms_total = timed(lambda: step(dev_frames))
     launches = msda.launch_count() - l0
+    if sampler:
+        sampler.mark_end()
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed(lambda: float(step(host.to(dev, non_blocking=True)).item()))
     if rank == 0:
@@ -448,6 +469,9 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
     warm = max(args.warmup, 3)
     for _ in range(warm):
         step(dev_frames, targets)
@@ -460,13 +484,16 @@ def main():
         step(dev_frames, targets)
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.stop()
+        if sampler:
+            sampler.stop()
         return
 
     # (1) device-resident throughput
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
-        sampler.start()
+        sampler.mark_begin()
     ms_total = timed(lambda: step(dev_frames, targets), args.steps)
+    if sampler:
+        sampler.mark_end()
     clocks = sampler.stop() if sampler else None
     value = bpg * world * args.steps / (ms_total / 1e3)
 

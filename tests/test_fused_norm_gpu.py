@@ -86,7 +86,8 @@ def test_colsum_and_fused_linear(dev):
     from trackformer_b200 import ext
     from trackformer_b200.fused_linear import linear
     m = ext.load()
-    for rows, c in ((22223, 256), (5000, 384), (4097, 1024), (3, 128), (6000, 288), (100, 1000)):
+    for rows, c in ((22223, 256), (5000, 384), (4097, 1024), (3, 128), (6000, 288), (100, 1000), (300, 256), (2048, 4),
+                    (2049, 8), (129, 36)):
         x = torch.randn(rows, c, device=dev)
         got = m.colsum(x)
         torch.testing.assert_close(got, x.double().sum(0).float(), rtol=1e-4, atol=1e-3)

@@ -99,3 +99,21 @@ def test_gradient_handover_equals_accumulation(oracle_op):
         assert p.grad.data_ptr() >= gather.flat_grad.data_ptr()          # the flat views are back in place
     torch.testing.assert_close(gather.flat_grad[~pads], accumulate.flat_grad[~pads], rtol=0, atol=0)
     assert float(gather.flat_grad[~pads].abs().sum()) > 0
+
+
+def test_seed_pool_hands_out_distinct_views_and_falls_back():
+    """seeds.py: one draw per step, consecutive one-element views; outside a step (or past the pool) a per-call draw."""
+    from trackformer_b200 import seeds
+    seeds.end_step()
+    a = seeds.next_seed("cpu")
+    assert a.shape == (1,) and a.dtype == torch.int64
+    seeds.begin_step("cpu")
+    views = [seeds.next_seed("cpu") for _ in range(seeds._POOL_SIZE + 3)]
+    pool = seeds._pool
+    assert all(v.shape == (1,) for v in views)
+    assert views[0].data_ptr() == pool.data_ptr() and views[1].data_ptr() == pool.data_ptr() + 8
+    assert views[-1].data_ptr() not in range(pool.data_ptr(), pool.data_ptr() + 8 * seeds._POOL_SIZE)   # fell back
+    old = views[0].clone()
+    seeds.begin_step("cpu")                                   # a new pool is a new tensor: earlier views stay valid
+    assert torch.equal(views[0], old)
+    seeds.end_step()
