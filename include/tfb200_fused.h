@@ -174,6 +174,50 @@ int tfb200_small_attn_bwd_f32(const float* q, const float* k, const float* v, co
                               float* dq, float* dk, float* dv, float* delta_ws, int B, int H, int L,
                               const int64_t* strides16, float scale, float keep_prob, void* stream);
 
+/* One frame of the online tracker's bookkeeping on the device (csrc/track_step.cu; reference models/tracker.py:266-548:
+ * score thresholds 337-373 / 425-436, both NMS passes 388-406 / 494-515, public-detection gating 122-164, ReID 166-264,
+ * results 533-545, reid_sim_only 547-548).  One CTA takes every decision of Tracker.step in the reference's order.
+ *
+ * State is a struct of arrays in track order: entries [0, n_active) are the active tracks, [n_active, n_active +
+ * n_inactive) the inactive ones, both in the reference's list order.  header = {n_active, n_inactive, track_num,
+ * num_reids, n_query_next, error, n_results, 0}.  `in` is CONSUMED (it is the kernel's work table, rows beyond the
+ * tracks are used for this frame's object queries: capacity >= n_active + n_inactive + nq, <= 2048); `out` receives
+ * the new state, `q_boxes` / `q_embeds` the track queries of the next frame (active tracks, then the inactive ones that
+ * survive the patience / positive-area test, boxes as cx, cy, w, h divided by the image size), and `result` the header
+ * followed by n_results rows of 8 words {id, obj_ind, score, x0, y0, x1, y1, 0} (ints and fp32 bit patterns).
+ * error: 1 = n_query does not match the state, 2 = capacity.                                                         */
+typedef struct TfbTrackState {
+  int32_t* header;             /* [8] */
+  int32_t* ids;                /* [capacity] */
+  float* pos;                  /* [capacity][4]  x0, y0, x1, y1 in pixels */
+  float* anchor;               /* [capacity][4]  position at the start of the step (Track.last_pos[-1]) */
+  float* score;                /* [capacity] */
+  int32_t* obj_ind;            /* [capacity] */
+  int32_t* count_inactive;     /* [capacity] */
+  int32_t* count_termination;  /* [capacity] */
+  float* bank;                 /* [capacity][hidden] last output embedding of every track */
+} TfbTrackState;
+
+typedef struct TfbTrackStepArgs {
+  const float* rows;           /* [n_query + nq][6] packed detections of this frame (tfb200_detect_postprocess_f32) */
+  const float* hs_embeds;      /* [n_query + nq][hidden] decoder output embeddings */
+  const float* public_dets;    /* [n_public][4] pixel xyxy, or NULL */
+  TfbTrackState in, out;
+  float* q_boxes;              /* [capacity][4] */
+  float* q_embeds;             /* [capacity][hidden] */
+  int32_t* result;             /* [8 + 8 * capacity] */
+  int32_t* iscratch;           /* [16 * capacity] */
+  float* fscratch;             /* [8 * capacity + capacity * max(nq, n_public, 1)] */
+  double* dscratch;            /* [4 * capacity] */
+  double inactive_patience, reid_sim_threshold;
+  float detection_obj_score_thresh, track_obj_score_thresh, reid_score_thresh, detection_nms_thresh, track_nms_thresh;
+  int32_t capacity, hidden, nq, n_query, n_public, img_h, img_w;
+  int32_t overflow_boxes, public_mode /* 0 off, 1 center_distance, 2 min_iou_0_5 */, reid_greedy_matching,
+      reid_sim_only, steps_termination, detection_nms_on, track_nms_on;
+} TfbTrackStepArgs;
+
+int tfb200_track_step_f32(const TfbTrackStepArgs* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -168,3 +168,118 @@ def test_graph_replay_outputs_match_eager_forward(dev):
         assert g2[name].shape == o2[name].shape
         torch.testing.assert_close(g2[name], o2[name], rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(ghs2, hs2, rtol=1e-3, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------ bookkeeping on the device (row f3)
+@pytest.mark.parametrize("case", list(tf.CASES))
+def test_device_tracker_matches_reference(dev, case):
+    """DeviceTracker: state on the GPU, one launch of csrc/track_step.cu per frame, one read-back of the result rows --
+    against the sequences recorded from the reference Tracker (every branch of Tracker.step)."""
+    from trackformer_b200.deformable_detr import DeformablePostProcess
+    from trackformer_b200.device_tracker import DeviceTracker
+    out = tf.run_case(DeviceTracker, DeformablePostProcess(), case, device=dev)
+    check_against_gold(out, case, rtol=1e-5)
+
+
+@pytest.mark.parametrize("case", list(tf.CASES))
+@pytest.mark.parametrize("seed", [1, 2])
+def test_device_tracker_equals_host_tracker_on_other_scenes(dev, case, seed):
+    from trackformer_b200.deformable_detr import DeformablePostProcess
+    from trackformer_b200.device_tracker import DeviceTracker
+    from trackformer_b200.tracker import Tracker
+    a = tf.run_case(Tracker, DeformablePostProcess(), case, device=dev, seed=seed)
+    b = tf.run_case(DeviceTracker, DeformablePostProcess(), case, device=dev, seed=seed)
+    for key in a:
+        if key == "rows":
+            np.testing.assert_array_equal(a[key][:, :3], b[key][:, :3], err_msg=key)
+            np.testing.assert_allclose(a[key][:, 3:], b[key][:, 3:], rtol=1e-6, atol=1e-4)
+        else:
+            np.testing.assert_array_equal(a[key], b[key], err_msg=f"{case}/{seed}: {key}")
+
+
+@pytest.mark.parametrize("multi_frame", [False, True])
+def test_device_tracker_over_graph_replay_equals_host_tracker(dev, multi_frame):
+    """the real detector under CUDA-graph replay: the SAME padded program feeds both trackers, so the decisions of the
+    device kernel and of the host bookkeeping must coincide exactly (ids, frames, obj_ind, boxes, scores)"""
+    from trackformer_b200.deformable_detr import DeformablePostProcess
+    from trackformer_b200.device_tracker import DeviceTracker
+    from trackformer_b200.graphed_detector import GraphedDetector
+    from trackformer_b200.tracker import Tracker
+    build, size = _build(dev), (128, 160)
+    thr = _probe_threshold(build, dev, multi_frame, size)
+    cfg = dict(detection_obj_score_thresh=thr, track_obj_score_thresh=thr * 0.97, reid_score_thresh=thr * 0.99,
+               inactive_patience=3, reid_sim_threshold=2.0, detection_nms_thresh=0.7, track_nms_thresh=0.7)
+    outs = []
+    for base in (Tracker, DeviceTracker):
+        class Graphed(base):
+            def __init__(self, model, post, cfg_, attn):
+                super().__init__(GraphedDetector(model, bucket=16), post, cfg_, attn)
+        outs.append(tf.run_model_sequence(build, Graphed, DeformablePostProcess(), cfg, size=size, n_frames=6,
+                                          device=dev, multi_frame=multi_frame))
+    host, device = outs
+    assert len(host["rows"]) > 0
+    for key in ("num_reids", "track_num", "frame_index", "active_ids", "inactive_ids", "inactive_counts"):
+        np.testing.assert_array_equal(host[key], device[key], err_msg=key)
+    np.testing.assert_array_equal(host["rows"][:, :3], device["rows"][:, :3])
+    np.testing.assert_allclose(host["rows"][:, 3:], device["rows"][:, 3:], rtol=1e-6, atol=1e-6)
+
+
+def test_device_tracker_many_targets(dev):
+    """150 simultaneous targets: buffers grow 256 -> 512 rows, NMS and the rank sort run over hundreds of boxes"""
+    from trackformer_b200.deformable_detr import DeformablePostProcess
+    from trackformer_b200.device_tracker import DeviceTracker
+    from trackformer_b200.tracker import Tracker
+
+    class Many(torch.nn.Module):
+        num_queries, overflow_boxes = 150, True
+
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+
+        def forward(self, img, targets=None, prev_features=None):
+            d = self.p.device
+            k = 0 if targets is None else len(targets[0]["track_query_boxes"])
+            g = torch.Generator().manual_seed(3)
+            centres = torch.rand(150, 2, generator=g) * 0.8 + 0.1
+            sizes = torch.rand(150, 2, generator=g) * 0.1 + 0.02
+            boxes = torch.cat([centres, sizes], 1).to(d)
+            logits = torch.full((k + 150, 4), -5.0, device=d)
+            logits[:, 0] = torch.linspace(0.5, 3.0, k + 150, device=d)
+            embeds = torch.arange(k + 150, dtype=torch.float32, device=d)[:, None].expand(-1, 8).contiguous()
+            if k:
+                boxes = torch.cat([targets[0]["track_query_boxes"], boxes], 0)
+                logits[k:, 0] = -2.0
+                embeds[:k] = targets[0]["track_query_hs_embeds"]
+            return {"pred_logits": logits[None], "pred_boxes": boxes[None], "hs_embed": embeds[None]}, None, None, None, None
+
+    cfg = tf.tracker_cfg("default")
+    cfg.update(detection_nms_thresh=0.3, track_nms_thresh=0.5)
+    blob = {"img": torch.zeros(1, 3, 8, 8), "orig_size": torch.tensor([[1000, 1000]]), "dets": torch.zeros(1, 0, 4)}
+    got = []
+    for cls in (Tracker, DeviceTracker):
+        tr = cls(Many().to(dev), {"bbox": DeformablePostProcess()}, cfg, False)
+        for _ in range(3):
+            tr.step(blob)
+        got.append(tf.summarise(tr))
+        if cls is DeviceTracker:
+            assert tr._bufs["capacity"] == 512
+    assert 20 < len(got[0]["active_ids"]) < 150               # the NMS really removed overlapping targets
+    for key in got[0]:
+        if key == "rows":
+            np.testing.assert_array_equal(got[0][key][:, :3], got[1][key][:, :3])
+            np.testing.assert_allclose(got[0][key][:, 3:], got[1][key][:, 3:], rtol=1e-6, atol=1e-4)
+        else:
+            np.testing.assert_array_equal(got[0][key], got[1][key], err_msg=key)
+
+
+def test_track_step_abi_rejects_bad_arguments(dev):
+    import ctypes
+    from trackformer_b200 import ext
+    from trackformer_b200.device_tracker import _ArgsC
+    ext.load()
+    lib = ctypes.CDLL(ext.library_path())
+    f = lib.tfb200_track_step_f32
+    f.argtypes, f.restype = [ctypes.POINTER(_ArgsC), ctypes.c_void_p], ctypes.c_int
+    assert f(None, None) == -1
+    assert f(ctypes.byref(_ArgsC()), None) == -1

@@ -32,10 +32,12 @@ def main():
     ap.add_argument("--multi-frame", action="store_true")
     ap.add_argument("--bucket", type=int, default=32)
     ap.add_argument("--no-tf32", action="store_true")
+    ap.add_argument("--skip-eager", action="store_true", help="only the CUDA-graph detector")
     args = ap.parse_args()
     from trackformer_b200.deformable_detr import DeformablePostProcess
     from trackformer_b200.graphed_detector import GraphedDetector
     from trackformer_b200.model_factory import build_model, default_args
+    from trackformer_b200.device_tracker import DeviceTracker
     from trackformer_b200.tracker import Tracker
 
     dev = torch.device("cuda:0")
@@ -56,9 +58,9 @@ def main():
                reid_greedy_matching=False)
     size = torch.tensor([[args.height, args.width]])
 
-    def run(detector):
+    def run(detector, tracker_cls=Tracker):
         post = DeformablePostProcess()
-        tr = Tracker(detector, {"bbox": post}, cfg, False)
+        tr = tracker_cls(detector, {"bbox": post}, cfg, False)
         tr.reset()
         # frame 0: start exactly --tracks tracks
         with torch.no_grad():
@@ -69,7 +71,7 @@ def main():
         tr.detection_obj_score_thresh = float((s[args.tracks - 1] + s[args.tracks]) / 2)
         tr.step({"img": frames[0], "orig_size": size, "dets": torch.zeros(1, 0, 4)})
         tr.detection_obj_score_thresh = 2.0
-        assert len(tr._active) == args.tracks, len(tr._active)
+        assert len(tr.tracks) == args.tracks, len(tr.tracks)
         times = []
         for i in range(args.warmup + args.frames):
             torch.cuda.synchronize()
@@ -78,12 +80,13 @@ def main():
             torch.cuda.synchronize()
             if i >= args.warmup:
                 times.append((time.perf_counter() - t0) * 1e3)
-        assert len(tr._active) == args.tracks
+        assert len(tr.tracks) == args.tracks
         return times
 
-    eager = run(model)
     det = GraphedDetector(model, bucket=args.bucket)
     graphed = run(det)
+    eager = graphed if args.skip_eager else run(model)
+    device = run(GraphedDetector(model, bucket=args.bucket), DeviceTracker)      # decisions in csrc/track_step.cu
     line = {
         "what": "Tracker.step latency, host frame in -> results out", "frames": args.frames, "warmup": args.warmup,
         "config": {"workload": f"tracking{' multi-frame' if args.multi_frame else ''} 1x3x{args.height}x{args.width}, "
@@ -91,9 +94,13 @@ def main():
                    "tf32": not args.no_tf32},
         "eager_ms": {"median": float(np.median(eager)), "p10": float(np.percentile(eager, 10)), "p90": float(np.percentile(eager, 90))},
         "graph_ms": {"median": float(np.median(graphed)), "p10": float(np.percentile(graphed, 10)), "p90": float(np.percentile(graphed, 90))},
+        "graph_device_tracker_ms": {"median": float(np.median(device)), "p10": float(np.percentile(device, 10)),
+                                    "p90": float(np.percentile(device, 90))},
         "eager_fps": 1e3 / float(np.median(eager)), "graph_fps": 1e3 / float(np.median(graphed)),
+        "graph_device_tracker_fps": 1e3 / float(np.median(device)),
         "graph_captures": det.captures, "graph_replays": det.replays,
         "h2d_bytes_per_frame": int(frames[0].numel() * 4), "d2h_bytes_per_frame": int((args.tracks + model.num_queries) * 6 * 4),
+        "d2h_bytes_per_frame_device_tracker": int((8 + 8 * (args.tracks + model.num_queries)) * 4),
     }
     print(json.dumps(line))
 
