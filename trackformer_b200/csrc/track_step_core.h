@@ -362,6 +362,7 @@ TS_FN void ts_step(const TfbTrackStepArgs& a, Shared& sh) {
   // ---- F. public-detection gating (tracker.py:122-164)
   if (a.public_mode != 0) {
     const int nd = sh.nd, np = a.public_dets ? a.n_public : 0;
+    TS_SYNC();                                  // every thread has read sh.nd before thread 0 rewrites it below
     if (nd > 0 && np > 0) {
       for (int e = tid; e < nd * np; e += nt) {
         const int i = e / np, j = e % np;

@@ -13,6 +13,10 @@ track ids, `obj_ind`, `num_reids`, frame sets, boxes and scores.  What differs i
     queries the next forward takes) and never uploads anything but the image and, if used, the public detections.
 
 CUDA only: on CPU tensors `step` raises (use `Tracker`, whose bookkeeping is host code by design).
+
+Differences a user can see: the debug logger receives the FRAME and INIT TRACK IDS lines only (the per-decision lines
+of tracker.py:375-379, 399-402, 232-235 would need the decisions on the host); `tracks` / `inactive_tracks` between
+frames cost one extra download of the state; tracks + object queries are limited to 2048 rows per frame.
 """
 import ctypes
 from collections import deque
