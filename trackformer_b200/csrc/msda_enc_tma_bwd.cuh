@@ -101,6 +101,11 @@ __device__ __forceinline__ void eb_slot_pass(uint32_t sw_addr, uint32_t sa_addr,
   unsigned gA = 0u, gB = 0u;                                     // element offsets of the rows the pending sums belong to
   int nzA = 0, nzB = 0;                                          // OR of the coefficient bits seen since the last flush
   const unsigned magic = (65536u + unsigned(BW) - 1u) / unsigned(BW);
+  // box row (y * BW + x) -> element offset of that pixel in the head's value / grad_value plane
+  auto to_global = [&](unsigned h) -> unsigned {
+    const unsigned ry = (h * magic) >> 16, rx = h - ry * unsigned(BW);
+    return gbox + ry * rowpitch + rx * gstride;
+  };
   const float* gp = gout0;
   asm volatile("" : "+l"(gp));                                   // opaque: keep the pointer, do not rematerialise it
   const size_t gstep = size_t(gq_stride) * 4;
@@ -143,20 +148,19 @@ __device__ __forceinline__ void eb_slot_pass(uint32_t sw_addr, uint32_t sa_addr,
       const unsigned rowA = o & 0x1FFu, rowB = (o >> 9) & 0x1FFu;
       la = rowA != 0x1FFu; lb = rowB != 0x1FFu;
       codes = o >> 18;
-      const unsigned ry = (rowA * magic) >> 16, rx = rowA - ry * unsigned(BW);
-      const unsigned gr = gbox + ry * rowpitch + rx * gstride;  // (meaningful when both sets load = reload)
-      const bool reload = la && lb;
-      ngA = reload ? gr : (la ? gB + gstride : gA);
-      ngB = reload ? gr + gstride : (lb ? gA + gstride : gB);
+      ngA = la ? rowA : gA;                                     // staged: gA / gB hold the BOX ROW of the column a set keeps;
+      ngB = lb ? rowB : gB;                                     // it is turned into a global offset only when the set is flushed
     }
     // a set that is about to be reloaded first sends what it has collected for its old rows
     if (la && (unsigned(nzA) << 1) != 0u) {
-      red2(const_cast<float*>(row_ptr(gvh, gA)), GA1);
-      red2(const_cast<float*>(row_ptr(gvh, gA + rowpitch)), GA3);
+      const unsigned f = GLOBAL ? gA : to_global(gA);
+      red2(const_cast<float*>(row_ptr(gvh, f)), GA1);
+      red2(const_cast<float*>(row_ptr(gvh, f + rowpitch)), GA3);
     }
     if (lb && (unsigned(nzB) << 1) != 0u) {
-      red2(const_cast<float*>(row_ptr(gvh, gB)), GB1);
-      red2(const_cast<float*>(row_ptr(gvh, gB + rowpitch)), GB3);
+      const unsigned f = GLOBAL ? gB : to_global(gB);
+      red2(const_cast<float*>(row_ptr(gvh, f)), GB1);
+      red2(const_cast<float*>(row_ptr(gvh, f + rowpitch)), GB3);
     }
     gA = ngA; gB = ngB;
     if (GLOBAL) {
@@ -201,12 +205,14 @@ __device__ __forceinline__ void eb_slot_pass(uint32_t sw_addr, uint32_t sa_addr,
     }
   }
   if ((unsigned(nzA) << 1) != 0u) {
-    red2(const_cast<float*>(row_ptr(gvh, gA)), GA1);
-    red2(const_cast<float*>(row_ptr(gvh, gA + rowpitch)), GA3);
+    const unsigned f = GLOBAL ? gA : to_global(gA);
+    red2(const_cast<float*>(row_ptr(gvh, f)), GA1);
+    red2(const_cast<float*>(row_ptr(gvh, f + rowpitch)), GA3);
   }
   if ((unsigned(nzB) << 1) != 0u) {
-    red2(const_cast<float*>(row_ptr(gvh, gB)), GB1);
-    red2(const_cast<float*>(row_ptr(gvh, gB + rowpitch)), GB3);
+    const unsigned f = GLOBAL ? gB : to_global(gB);
+    red2(const_cast<float*>(row_ptr(gvh, f)), GB1);
+    red2(const_cast<float*>(row_ptr(gvh, f + rowpitch)), GB3);
   }
 }
 

@@ -104,6 +104,7 @@ class DeviceTracker(Tracker):
             "fscratch": torch.zeros(8 * capacity + capacity * width, dtype=torch.float32, device=dev),
             "dscratch": torch.zeros(4 * capacity, dtype=torch.float64, device=dev),
             "host": torch.zeros(8 + 8 * capacity, dtype=torch.int32),
+            "image_id": torch.tensor([1], device=dev),
         }
         if dev.type == "cuda":
             bufs["host"] = bufs["host"].pin_memory()
@@ -166,7 +167,7 @@ class DeviceTracker(Tracker):
         target = None
         if n_query:
             b = self._bufs
-            target = [{"track_query_boxes": b["q_boxes"][:n_query], "image_id": torch.tensor([1]).to(dev),
+            target = [{"track_query_boxes": b["q_boxes"][:n_query], "image_id": b["image_id"],
                        "track_query_hs_embeds": b["q_embeds"][:n_query]}]
         outputs, _, features, _, _ = self.obj_detector(img, target, self._prev_features[0])
         hs_embeds = outputs["hs_embed"][0].float().contiguous()
