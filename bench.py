@@ -498,11 +498,19 @@ def main():
     value = bpg * world * args.steps / (ms_total / 1e3)
 
     # (2) end to end: pinned host frame -> device every step, loss read back every step
-    def e2e_step():
-        frames = host_frames.to(dev, non_blocking=True)
-        return float(step(frames, targets).item())
-    e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    #     The copy of step i + 1's frame is started (TrainStep.prefetch: side stream, staging buffer) right after step i
+    #     has been enqueued and before its loss is read, so it runs under step i -- the usual data-loader pipelining.
+    #     The timed region holds exactly K copies, K steps and K loss reads: the first frame's copy is issued (and
+    #     exposed) inside it, nothing is prefetched for a step outside it.
+    def e2e_region(k):
+        step.prefetch(host_frames)
+        for i in range(k):
+            loss = step(None, targets)         # consumes the prefetched frame
+            if i + 1 < k:
+                step.prefetch(host_frames)     # next step's frame, overlapped with this step
+            float(loss.item())
+    e2e_region(2)
+    ms_e2e = timed(lambda: e2e_region(args.steps), 1)
     e2e_value = bpg * world * args.steps / (ms_e2e / 1e3)
 
     # (2b) the general path: ground-truth box counts that change every step (forward graph + sync-free loss + backward
@@ -646,7 +654,9 @@ def main():
                    "weights": "random init", "gt_boxes_per_frame": N_GT,
                    "l2": "no explicit flush: one step streams >1 GB of activations/weights, far above the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": host_frames.numel() * 4,
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                "input_copy": "every step's frame copied from pinned host memory inside the timed region, on a side "
+                              "stream under the previous step (TrainStep.prefetch); loss read back every step"},
         "gpu_launches": int(launches) * world,
         "clocks": clocks,
         "roofline": roofline,

@@ -117,3 +117,25 @@ def test_seed_pool_hands_out_distinct_views_and_falls_back():
     seeds.begin_step("cpu")                                   # a new pool is a new tensor: earlier views stay valid
     assert torch.equal(views[0], old)
     seeds.end_step()
+
+
+def test_prefetch_hands_frames_to_the_next_step(oracle_op):
+    """host logic of TrainStep.prefetch on CPU: the staged frames are consumed exactly once"""
+    import copy
+    from trackformer_b200.train_step import TrainStep
+    model, criterion = build(False, False, enc_layers=1, dec_layers=2, num_queries=20, dropout=0.0)
+    mf.canonical_weights_(model, 0)
+    model.train()
+    model_b = copy.deepcopy(model)
+    x = mf.make_images(3, [(96, 128)])[0][None]
+    targets = mf.make_targets(4, 1, 3)
+    a = TrainStep(model, criterion, None, use_graphs=False)
+    b = TrainStep(model_b, criterion, None, use_graphs=False)
+    with pytest.raises(ValueError, match="prefetch"):
+        a(None, targets)
+    a.prefetch(x)
+    la, lb = a(None, targets), b(x, targets)
+    torch.testing.assert_close(la, lb, rtol=0, atol=0)
+    torch.testing.assert_close(a.flat_grad, b.flat_grad, rtol=0, atol=0)
+    with pytest.raises(ValueError, match="prefetch"):
+        a(None, targets)

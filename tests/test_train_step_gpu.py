@@ -148,3 +148,36 @@ def test_flat_parameter_layout_and_reference_groups(cuda_device):
         assert float((a - b).abs().max()) <= 3 * 2 * 2e-4 * 1.01, k
         if float(b.norm()) > 1e-2:
             assert float((a - b).norm() / b.norm()) < 2e-3, k
+
+
+def test_prefetched_frames_equal_directly_passed_frames(cuda_device):
+    """TrainStep.prefetch: pinned host frames copied on a side stream into a staging buffer, consumed by step(None, ...).
+    Same losses and gradients as handing the frames over directly -- on the full-step graph, on the two-graph fallback
+    (different box count) and on the eager path -- also when the next prefetch is issued before the loss is read."""
+    from trackformer_b200.train_step import TrainStep
+    dev = cuda_device
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    g = torch.Generator().manual_seed(6)
+    host = [torch.randn(1, 3, 192, 256, generator=g).pin_memory() for _ in range(4)]
+    counts = (5, 5, 7, 5)
+    for use_graphs in (True, False):
+        model, criterion = small_model(dev)
+        model_d = copy.deepcopy(model)
+        kw = dict(use_graphs=use_graphs)
+        if use_graphs:
+            kw.update(example_frames=host[0].to(dev), example_targets=targets_for(dev, 0, 5))
+        pre = TrainStep(model, criterion, None, **kw)
+        direct = TrainStep(model_d, criterion, None, **kw)
+        with pytest.raises(ValueError, match="prefetch"):
+            pre(None, targets_for(dev, 0, 5))
+        pre.prefetch(host[0])
+        for i, n in enumerate(counts):
+            tg = targets_for(dev, 40 + i, n)
+            loss_p = pre(None, tg)
+            if i + 1 < len(host):
+                pre.prefetch(host[i + 1])               # before the loss of step i is read: overlaps with step i
+            loss_p = loss_p.clone()
+            loss_d = direct(host[i].to(dev), tg)
+            torch.testing.assert_close(loss_p, loss_d, rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(pre.flat_grad, direct.flat_grad, rtol=1e-4, atol=1e-6 * float(direct.flat_grad.abs().max()) + 1e-9)

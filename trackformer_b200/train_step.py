@@ -70,6 +70,8 @@ class TrainStep:
         # paths (full-step graph / two graphs / eager) in the same step and still run the same collective sequence.
         self.s_num_boxes = None
         self.g_fwd = self.g_bwd = self.g_full = None
+        # input prefetch (see prefetch()): staging buffer + copy stream, created on first use
+        self._staged = self._staging = self._copy_stream = self._staged_ready = self._staging_free = None
         # gradient hand-over instead of per-parameter accumulation (see _backward_into_flat)
         self.gather_grads = os.environ.get("TFB200_GATHER_GRADS", "1") != "0"
 
@@ -348,8 +350,40 @@ class TrainStep:
             return self.criterion.num_boxes_device(targets, device, out=self.s_num_boxes)
         return None
 
-    def __call__(self, frames: torch.Tensor, targets: list) -> torch.Tensor:
+    def prefetch(self, frames: torch.Tensor) -> None:
+        """Start moving the NEXT step's frames (pinned host memory) to the device on a side stream, so that the copy
+        runs under the step that is executing; the next ``step(None, targets)`` consumes them.  The data loader's job in
+        a training loop (the reference moves each batch synchronously at the top of the iteration, engine.py:126-128)."""
         dev = self.flat_grad.device
+        if dev.type != "cuda":
+            self._staged = frames
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+            self._staged_ready, self._staging_free = torch.cuda.Event(), torch.cuda.Event()
+            self._staging_free.record(torch.cuda.current_stream(dev))
+        if self._staging is None or self._staging.shape != frames.shape or self._staging.dtype != frames.dtype:
+            self._staging = torch.empty(frames.shape, dtype=frames.dtype, device=dev)
+        cs = self._copy_stream
+        cs.wait_event(self._staging_free)               # the previous step has finished reading the staging buffer
+        with torch.cuda.stream(cs):
+            self._staging.copy_(frames, non_blocking=True)
+        self._staged_ready.record(cs)
+        self._staged = self._staging
+
+    def _release_staging(self, dev):
+        if self._staging_free is not None:
+            self._staging_free.record(torch.cuda.current_stream(dev))
+
+    def __call__(self, frames: Optional[torch.Tensor], targets: list) -> torch.Tensor:
+        dev = self.flat_grad.device
+        staged = frames is None
+        if staged:
+            if self._staged is None:
+                raise ValueError("step(None, targets) needs frames handed over with prefetch() first")
+            frames, self._staged = self._staged, None
+            if dev.type == "cuda":
+                torch.cuda.current_stream(dev).wait_event(self._staged_ready)
         full = self.g_full is not None and tuple(len(t["labels"]) for t in targets) == self.full_sizes
         # one scalar all-reduce per step on EVERY path, before anything else (same collective order on all ranks)
         num_boxes = self._normaliser(targets, dev) if (self.world > 1 or full) else None
@@ -357,6 +391,9 @@ class TrainStep:
         if full:
             if frames is not self.static_frames:
                 self.static_frames.copy_(frames, non_blocking=True)     # device or pinned-host source
+            if staged and dev.type == "cuda":
+                self._release_staging(dev)
+                staged = False
             for st, t in zip(self.s_targets, targets):
                 if t["boxes"] is not st["boxes"]:
                     st["boxes"].copy_(t["boxes"], non_blocking=True)
@@ -379,6 +416,9 @@ class TrainStep:
         elif self.g_fwd is not None:
             if frames is not self.static_frames:
                 self.static_frames.copy_(frames, non_blocking=True)     # device or pinned-host source
+            if staged and dev.type == "cuda":
+                self._release_staging(dev)
+                staged = False
             self.g_fwd.replay()
             logits = self.s_logits.detach().requires_grad_(True)
             boxes = self.s_boxes.detach().requires_grad_(True)
@@ -411,4 +451,6 @@ class TrainStep:
         elif self.flat_optimizer is not None:
             norm = torch.linalg.vector_norm(self.flat_grad) if self.max_norm > 0 else None
             self.flat_optimizer.step(norm, self.max_norm)
+        if staged and dev.type == "cuda":                # eager paths read the staging buffer directly: free it now
+            self._release_staging(dev)
         return loss.detach()
