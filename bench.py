@@ -354,12 +354,31 @@ def c5_arm(args, rank, local_rank, world):
                 "e2e": {"value": bpg * world * args.steps / (ms_e2e / 1e3), "unit": "frames/s",
                         "h2d_bytes_per_step": host.numel() * 4, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches) * world, "clocks": clocks, "roofline": None, "cpu_baseline": None}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 # --------------------------------------------------------------------------------------------- main
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its "NCCL version ..." banner
+    to stdout whenever NCCL_DEBUG is VERSION or WARN -- NCCL_DEBUG_FILE is only honoured from INFO up), so file
+    descriptor 1 is pointed at stderr for the whole run and the line goes out through a private copy of the real one."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -380,6 +399,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=2)
     args = ap.parse_args()
+    _claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -406,7 +426,7 @@ def main():
                                  "sample": f"{steps} full train step(s), pure-PyTorch grid_sample MSDeformAttn (oracle/torch_ref.py)"},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -670,7 +690,7 @@ def main():
         "msda_ms_per_step": round(msda_ms, 4),
         "cpu_baseline": cpu_baseline,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
