@@ -139,3 +139,45 @@ def test_prefetch_hands_frames_to_the_next_step(oracle_op):
     torch.testing.assert_close(a.flat_grad, b.flat_grad, rtol=0, atol=0)
     with pytest.raises(ValueError, match="prefetch"):
         a(None, targets)
+
+
+def test_weighted_loss_total_from_stacked_vectors_equals_the_entry_sum(oracle_op):
+    """TrainStep._loss: (stack(ce, l1, giou) * weights).sum() == sum(loss_dict[k] * weight_dict[k]) (engine.py:139-140),
+    values and gradients"""
+    from trackformer_b200.criterion import LossDict
+    from trackformer_b200.train_step import TrainStep
+    model, criterion = build(False, False, enc_layers=1, dec_layers=3, num_queries=20, dropout=0.0)
+    mf.canonical_weights_(model, 0)
+    model.train()
+    step = TrainStep(model, criterion, None, use_graphs=False)
+    x = mf.make_images(3, [(96, 128)])[0][None]
+    targets = mf.make_targets(4, 1, 3)
+    wd = criterion.weight_dict
+    assert sorted(k for k in wd if k.endswith("_1")) == ["loss_bbox_1", "loss_ce_1", "loss_giou_1"]
+    grads = []
+    for naive in (False, True):
+        logits, boxes = step.core(x)
+        logits, boxes = logits.detach().requires_grad_(True), boxes.detach().requires_grad_(True)
+        if naive:
+            d = criterion.forward_stacked(logits, boxes, targets)
+            assert isinstance(d, LossDict) and d.stacked is not None
+            total = sum(d[k] * wd[k] for k in d if k in wd)
+        else:
+            total = step._loss(logits, boxes, targets)
+        grads.append((total.detach(), *torch.autograd.grad(total, (logits, boxes))))
+    for a, b in zip(*grads):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-7)
+    # layers without an entry in weight_dict weigh nothing
+    wd_backup = dict(wd)
+    try:
+        for k in list(wd):
+            if k.endswith("_0"):
+                del wd[k]
+        step._loss_w_key = None
+        logits, boxes = step.core(x)
+        d = criterion.forward_stacked(logits, boxes, targets)
+        torch.testing.assert_close(step._loss(logits, boxes, targets), sum(d[k] * wd[k] for k in d if k in wd),
+                                   rtol=1e-5, atol=1e-7)
+    finally:
+        wd.clear()
+        wd.update(wd_backup)

@@ -43,6 +43,14 @@ class _SetLoss(torch.autograd.Function):
                                               num_boxes)
         return gl, gb, None, None, None, None, None, None, None, None, None
 
+class LossDict(dict):
+    """The loss dictionary of ``SetCriterion.forward_stacked`` (reference keys, detr.py:404-424) that also carries the
+    per-layer loss VECTORS ``stacked = (loss_ce [K], loss_bbox [K], loss_giou [K])`` its entries are views of: a
+    training step can then form the weighted total with three launches instead of one multiply and one add per
+    (loss, layer) entry forward and again backward (~110 single-element launches per step at K = 6)."""
+    stacked = None
+
+
 class SetCriterion(nn.Module):
     def __init__(self, num_classes, matcher, weight_dict, eos_coef, losses, focal_loss, focal_alpha,
                  focal_gamma, tracking, track_query_false_positive_eos_weight):
@@ -201,13 +209,14 @@ class SetCriterion(nn.Module):
         ce, l1, gi, card, cerr = _SetLoss.apply(logits, boxes, src2d, tgt2d, tgt_ids, tgt_boxes, off, n_gt,
                                                 num_boxes.reshape(1).float(), float(self.focal_alpha),
                                                 float(self.focal_gamma))
-        losses = {"loss_ce": ce[-1], "class_error": cerr[-1], "loss_bbox": l1[-1], "loss_giou": gi[-1],
-                  "cardinality_error": card[-1]}
+        losses = LossDict({"loss_ce": ce[-1], "class_error": cerr[-1], "loss_bbox": l1[-1], "loss_giou": gi[-1],
+                           "cardinality_error": card[-1]})
         for i in range(k - 1):
             losses[f"loss_ce_{i}"] = ce[i]
             losses[f"loss_bbox_{i}"] = l1[i]
             losses[f"loss_giou_{i}"] = gi[i]
             losses[f"cardinality_error_{i}"] = card[i]
+        losses.stacked = (ce, l1, gi)
         return losses
 
     def forward_stacked(self, logits, boxes, targets, num_boxes=None):
@@ -289,11 +298,12 @@ class SetCriterion(nn.Module):
             last = slice((k - 1) * per_layer, None)
             class_error = 100 - accuracy(logits[-1][bat[last], src[last]], gt_labels[last])[0]
 
-        losses = {"loss_ce": loss_ce[-1], "class_error": class_error, "loss_bbox": loss_bbox[-1],
-                  "loss_giou": loss_giou[-1], "cardinality_error": card[-1]}
+        losses = LossDict({"loss_ce": loss_ce[-1], "class_error": class_error, "loss_bbox": loss_bbox[-1],
+                           "loss_giou": loss_giou[-1], "cardinality_error": card[-1]})
         for i in range(k - 1):
             losses[f"loss_ce_{i}"] = loss_ce[i]
             losses[f"loss_bbox_{i}"] = loss_bbox[i]
             losses[f"loss_giou_{i}"] = loss_giou[i]
             losses[f"cardinality_error_{i}"] = card[i]
+        losses.stacked = (loss_ce, loss_bbox, loss_giou)
         return losses

@@ -339,8 +339,21 @@ class TrainStep:
                 v.zero_()
 
     def _loss(self, logits, boxes, targets, num_boxes=None):
+        """Weighted total of the criterion's entries (engine.py:139-140: sum(loss_dict[k] * weight_dict[k]))."""
         loss_dict = self.criterion.forward_stacked(logits, boxes, targets, num_boxes)
         wd = self.criterion.weight_dict
+        stacked = getattr(loss_dict, "stacked", None)
+        names = ("loss_ce", "loss_bbox", "loss_giou")
+        if stacked is not None and all(k in loss_dict for k in names) and \
+                not any(k in wd and not any(k == n or k.startswith(n + "_") for n in names) for k in loss_dict):
+            # the same sum over the per-layer loss vectors: stack, one multiply with the [3, K] weight table, one sum
+            k = stacked[0].shape[0]
+            key = (k, stacked[0].device)
+            if getattr(self, "_loss_w_key", None) != key:
+                rows = [[float(wd.get(f"{n}_{i}", 0.0)) for i in range(k - 1)] + [float(wd.get(n, 0.0))] for n in names]
+                self._loss_w = torch.tensor(rows, dtype=stacked[0].dtype, device=stacked[0].device)
+                self._loss_w_key = key
+            return (torch.stack(stacked) * self._loss_w).sum()
         return sum(loss_dict[k] * wd[k] for k in loss_dict if k in wd)
 
     def _normaliser(self, targets, device):
