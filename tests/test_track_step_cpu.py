@@ -216,3 +216,47 @@ def test_device_routine_equals_host_tracker_on_random_scenes(host_tracker, seed)
             np.testing.assert_allclose(a[key][:, 3:], b[key][:, 3:], rtol=1e-6, atol=1e-4)
         else:
             np.testing.assert_array_equal(a[key], b[key], err_msg=f"seed {seed}: {key}")
+
+
+def test_error_paths_of_the_step_routine(host_tracker):
+    """a state / query-count mismatch is reported through the header (error 1), too many rows through error 2 -- and the
+    Python side refuses to grow beyond the routine's 2048 rows"""
+    scene = tf.Scene()
+    det = tf.ScriptedDetector(scene)
+    tr = host_tracker(det, {"bbox": DeformablePostProcess()}, tf.tracker_cfg("default"), False)
+    blobs = list(tf.blobs(scene))
+    tr.step(blobs[0])
+    assert tr._n_query > 0
+    tr._n_query -= 1                                    # the detector will answer one track query too few
+    with pytest.raises((RuntimeError, AssertionError), match="error 1|shape|\\("):
+        tr.step(blobs[1])
+
+    class Huge(torch.nn.Module):
+        num_queries, overflow_boxes = 2100, True
+
+        def __init__(self):
+            super().__init__()
+            self.p = torch.nn.Parameter(torch.zeros(1))
+
+        def forward(self, img, targets=None, prev_features=None):
+            q = self.num_queries
+            return {"pred_logits": torch.full((1, q, 2), -5.0), "pred_boxes": torch.full((1, q, 4), 0.5),
+                    "hs_embed": torch.zeros(1, q, 4)}, None, None, None, None
+    big = host_tracker(Huge(), {"bbox": DeformablePostProcess()}, tf.tracker_cfg("default"), False)
+    with pytest.raises(RuntimeError, match="2048"):
+        big.step({"img": torch.zeros(1, 3, 8, 8), "orig_size": torch.tensor([[100, 100]]), "dets": torch.zeros(1, 0, 4)})
+
+
+def test_public_detections_without_a_dets_entry(host_tracker):
+    """blob without 'dets' while public detections are required: nothing may start (tracker.py:437-446 with no boxes)"""
+    scene = tf.Scene()
+    cfg = tf.tracker_cfg("public_center")
+    outs = []
+    for cls in (Tracker, host_tracker):
+        det = tf.ScriptedDetector(scene, overflow_boxes=False)
+        tr = cls(det, {"bbox": DeformablePostProcess()}, cfg, False)
+        for blob in list(tf.blobs(scene))[:3]:
+            blob.pop("dets")
+            tr.step(blob)
+        outs.append((tr.track_num, len(tr.results)))
+    assert outs[0] == outs[1] == (0, 0)
