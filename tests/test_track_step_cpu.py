@@ -260,3 +260,33 @@ def test_public_detections_without_a_dets_entry(host_tracker):
             tr.step(blob)
         outs.append((tr.track_num, len(tr.results)))
     assert outs[0] == outs[1] == (0, 0)
+
+
+def test_device_routine_under_the_padded_detector(host_tracker, monkeypatch):
+    """GraphedDetector's filler-padded program (eager on CPU) fed by the routine's own next-frame queries: same ids and
+    values as the host tracker over the same padded detector"""
+    from oracle.torch_ref import msda_core_torch
+    import trackformer_b200.msda_module as mm
+    from test_model_parity_cpu import build
+    from trackformer_b200.graphed_detector import GraphedDetector
+
+    class _OracleFn:
+        @staticmethod
+        def apply(value, shapes, loc, attn, step):
+            return msda_core_torch(value, shapes, loc, attn)
+    monkeypatch.setattr(mm, "MSDeformAttnFunction", _OracleFn)
+    gold = np.load(os.path.join(GOLD, "tracker_model_sequence.npz"))
+    cfg = {k: float(v) for k, v in zip(gold["cfg_keys"], gold["cfg_values"])}
+    cfg["prev_frame_dist"] = int(cfg["prev_frame_dist"])
+    outs = []
+    for base in (Tracker, host_tracker):
+        class Padded(base):
+            def __init__(self, model, post, cfg_, attn):
+                super().__init__(GraphedDetector(model, bucket=8, use_graphs=False), post, cfg_, attn)
+        outs.append(tf.run_model_sequence(build, Padded, DeformablePostProcess(), cfg))
+    a, b = outs
+    assert len(a["rows"]) > 0
+    for key in ("num_reids", "track_num", "frame_index", "active_ids", "inactive_ids", "inactive_counts"):
+        np.testing.assert_array_equal(a[key], b[key], err_msg=key)
+    np.testing.assert_array_equal(a["rows"][:, :3], b["rows"][:, :3])
+    np.testing.assert_allclose(a["rows"][:, 3:], b["rows"][:, 3:], rtol=1e-6, atol=1e-6)
