@@ -58,7 +58,11 @@ def _worker(rank, world, port, out_dir):
         assert step.world == world
         assert step.phased            # three-piece backward, one all-reduce per finished gradient slice
         frames, targets = _data(rank)
-        loss = step(frames, targets)
+        if rank == 1:                 # ranks may hand their frames over differently: same collectives either way
+            step.prefetch(frames)
+            loss = step(None, targets)
+        else:
+            loss = step(frames, targets)
         torch.save({"grad": step.flat_grad.clone(), "loss": loss}, os.path.join(out_dir, f"rank{rank}.pt"))
     finally:
         dist.destroy_process_group()
