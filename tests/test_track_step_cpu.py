@@ -186,7 +186,7 @@ class _RandomDetector(torch.nn.Module):
         return {"pred_logits": logits[None], "pred_boxes": boxes[None], "hs_embed": embeds[None]}, None, None, None, None
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(30))
 def test_device_routine_equals_host_tracker_on_random_scenes(host_tracker, seed):
     rng = np.random.RandomState(seed)
     cfg = dict(tf.BASE_CFG)
